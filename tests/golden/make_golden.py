@@ -1,0 +1,104 @@
+"""Generates the golden fixtures in this directory by running the reference's OWN, UNMODIFIED source files
+(/root/reference, imported through oracle/ref_shims.py) on seeded weights and inputs.  Runs only in the build
+container (the GPU box has no /root/reference); the fixtures travel instead.
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the config, the seed and the reference outputs (plus sub-sampled stage outputs); weights and
+inputs are regenerated from the seed by oracle/weights.py when the fixture is checked.
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_shims, weights  # noqa: E402
+
+CASES = {
+    # name: (grid step deg, batch, model kwargs, seed)
+    "forecaster_10deg_b2": dict(step=10, batch=2, seed=1, kw={}),
+    "forecaster_5deg_b1": dict(step=5, batch=1, seed=2, kw={}),
+    "forecaster_small_hidden64": dict(
+        step=10, batch=3, seed=3,
+        kw=dict(node_dim=64, edge_dim=64, num_blocks=3, hidden_dim_processor_node=64, hidden_dim_processor_edge=64,
+                hidden_dim_decoder=32, feature_dim=10, aux_dim=4),
+    ),  # fmt: skip
+}
+STAGE_STRIDE = 53  # stage outputs are stored for every 53rd mesh row only (keeps fixtures small)
+
+
+def grid(step):
+    return [(float(lat), float(lon)) for lat in range(-90, 90, step) for lon in range(0, 360, step)]
+
+
+def run_forecaster(R, name, spec):
+    lat_lons = grid(spec["step"])
+    kw = spec["kw"]
+    model = R.GraphWeatherForecaster(lat_lons, **kw).eval()
+    shapes = weights.forecaster_shapes(num_h3=model.encoder.h3_nodes.shape[0], **kw)
+    ref_sd = model.state_dict()
+    assert list(shapes.keys()) == list(ref_sd.keys()), "state_dict key contract drifted"
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), (k, v.shape, shapes[k])
+    sd = weights.make_state_dict(shapes, spec["seed"])
+    model.load_state_dict(sd)
+    fdim = kw.get("feature_dim", 78) + kw.get("aux_dim", 24)
+    x = weights.make_features(spec["batch"], len(lat_lons), fdim, spec["seed"])
+    with torch.no_grad():
+        enc_x, ei, ea = model.encoder(x)
+        proc_x = model.processor(enc_x, ei, ea)
+        out = model.decoder(proc_x, x[..., : model.feature_dim])
+        out2 = model(x)
+    assert torch.equal(out, out2)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        config=json.dumps(dict(step=spec["step"], batch=spec["batch"], seed=spec["seed"], kw=kw)),
+        out=out.numpy(),
+        enc_x_sub=enc_x.numpy()[::STAGE_STRIDE],
+        proc_x_sub=proc_x.numpy()[::STAGE_STRIDE],
+        enc_edge_index=model.encoder.graph.edge_index.numpy().astype(np.int32),
+        enc_edge_attr=model.encoder.graph.edge_attr.numpy(),
+        lat_edge_index_sum=np.array(model.encoder.latent_graph.edge_index.numpy().sum(axis=1)),
+        lat_edge_attr_sub=model.encoder.latent_graph.edge_attr.numpy()[::STAGE_STRIDE],
+        dec_edge_index_sub=model.decoder.graph.edge_index.numpy()[:, ::7].astype(np.int32),
+        dec_edge_attr_sub=model.decoder.graph.edge_attr.numpy()[::7],
+    )
+    print(name, "out", tuple(out.shape), "mean|out|", float(out.abs().mean()))
+
+
+def run_assimilator(R, name="assimilator_readme"):
+    """README.md:75-90 configuration with fixed seeds."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    obs = []
+    for lat in range(-90, 90, 7):
+        for lon in rng.uniform(0, 360, 100):
+            obs.append((float(lat), float(lon), float(rng.uniform())))
+    obs = obs + [(float(lat), float(lon), float(rng.uniform())) for lat in range(-90, 90, 45) for lon in range(0, 360, 24)]
+    obs_t = torch.tensor(obs, dtype=torch.float)
+    out_ll = grid(5)
+    model = R.GraphWeatherAssimilator(output_lat_lons=out_ll, analysis_dim=24).eval()
+    shapes = weights.forecaster_shapes(assimilator=True, output_dim=24)
+    ref_sd = model.state_dict()
+    assert list(shapes.keys()) == list(ref_sd.keys()), (set(shapes) ^ set(ref_sd))
+    sd = weights.make_state_dict(shapes, 4)
+    model.load_state_dict(sd)
+    x = weights.make_features(1, len(obs), 2, 4)
+    with torch.no_grad():
+        out = model(x, obs_t)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), config=json.dumps(dict(seed=4, analysis_dim=24, step=5)),
+                        obs=obs_t.numpy(), out=out.numpy())  # fmt: skip
+    print(name, "out", tuple(out.shape), "mean|out|", float(out.abs().mean()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    R = ref_shims.load_reference()
+    for n, s in CASES.items():
+        run_forecaster(R, n, s)
+    run_assimilator(R)

@@ -1,0 +1,47 @@
+"""Pins the CPU restatement (oracle/restate.py) to outputs of the reference's own unmodified code (tests/golden/*.npz)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, weights
+
+
+def _grid(step):
+    return [(float(lat), float(lon)) for lat in range(-90, 90, step) for lon in range(0, 360, step)]
+
+
+@pytest.mark.parametrize("name", ["forecaster_10deg_b2", "forecaster_small_hidden64", "forecaster_5deg_b1"])
+def test_restatement_matches_reference(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = json.loads(str(z["config"]))
+    kw = cfg["kw"]
+    ll = _grid(cfg["step"])
+    g = restate.build_forecaster_graphs(ll)
+    sd = weights.make_state_dict(weights.forecaster_shapes(**kw), cfg["seed"])
+    fdim = kw.get("feature_dim", 78)
+    x = weights.make_features(cfg["batch"], len(ll), fdim + kw.get("aux_dim", 24), cfg["seed"])
+    nb = kw.get("num_blocks", 9)
+    with torch.no_grad():
+        enc_x, ei, ea = restate.encoder_forward(sd, g, x)
+        proc_x = restate.processor_forward(sd, enc_x, ei, ea, nb)
+    out = restate.forecaster_forward(sd, g, x, feature_dim=fdim, num_blocks=nb)
+    # same ops in the same order on the same machine class: expect (near) bit equality; 1e-5 is the tolerance the
+    # reference's own equivalence tests use (tests/models/layers/test_efficient_batching.py:53,91)
+    assert np.abs(enc_x.numpy()[::53] - z["enc_x_sub"]).max() < 1e-5
+    assert np.abs(proc_x.numpy()[::53] - z["proc_x_sub"]).max() < 1e-5
+    assert out.shape == z["out"].shape
+    assert np.abs(out.numpy() - z["out"]).max() < 1e-5
+
+
+def test_assimilator_restatement_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "assimilator_readme.npz"))
+    cfg = json.loads(str(z["config"]))
+    g = restate.build_assimilator_graphs(_grid(cfg["step"]))
+    sd = weights.make_state_dict(weights.forecaster_shapes(assimilator=True, output_dim=cfg["analysis_dim"]), cfg["seed"])
+    obs = torch.from_numpy(z["obs"])
+    x = weights.make_features(1, obs.shape[0], 2, cfg["seed"])
+    out = restate.assimilator_forward(sd, g, x, obs)
+    assert np.abs(out.numpy() - z["out"]).max() < 1e-5
