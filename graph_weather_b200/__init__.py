@@ -1,0 +1,21 @@
+"""graph_weather_b200 -- the encode-process-decode GNN forward of openclimatefix/graph_weather, rebuilt for B200 (sm_100a).
+
+Public names mirror graph_weather/__init__.py:3-9 and graph_weather/models/__init__.py:3-17 for the hot path only.
+"""
+
+from .models import (  # noqa: F401
+    AssimilatorDecoder,
+    AssimilatorEncoder,
+    Decoder,
+    Encoder,
+    GraphWeatherAssimilator,
+    GraphWeatherAssimilatorConfig,
+    GraphWeatherForecaster,
+    GraphWeatherForecasterConfig,
+    Processor,
+)
+
+__all__ = [
+    "GraphWeatherForecaster", "GraphWeatherForecasterConfig", "GraphWeatherAssimilator", "GraphWeatherAssimilatorConfig",
+    "Encoder", "Processor", "Decoder", "AssimilatorEncoder", "AssimilatorDecoder",
+]  # fmt: skip

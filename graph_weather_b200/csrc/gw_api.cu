@@ -1,0 +1,796 @@
+// gw_api.cu -- the C ABI of libgwb200.so (include/gw_b200.h): plan, graph / weight upload, weight-constant
+// precompute, and the encode-process-decode forward expressed as chains of gw::GemmOp row ops.
+//
+// Algebra used (results equal the reference's up to fp32 summation order; SURVEY.md section 7 "dead work"):
+//   * layer 1 of every edge MLP is factored   W1 [x_s ; x_d ; e] = W1s x_s + W1d x_d + W1e e      (graph_net_block.py:131)
+//     so the per-edge K=768 contraction becomes two per-NODE products (P = x [W1s;W1d]^T) gathered in the epilogue
+//     plus a K=256 per-edge product; in the decoder x_d == 0 (assimilator_decoder.py:84,189-193) and e is constant,
+//     so layer 1 there needs no per-edge GEMM at all: relu(P[src] + E1).
+//   * batch-invariant tensors are computed once per weight set: edge_encoder(edge_attr) for the three graphs
+//     (encoder.py:206, :235-241; assimilator_decoder.py:175), node_encoder(h3_nodes) (encoder.py:199-205),
+//     and the constant layer-1 terms C1_enc / E1_dec.
+//   * rows whose results the reference discards are not computed: the encoder block's lat/lon node update
+//     (encoder.py:221-223), the decoder block's mesh node update and node_decoder on mesh rows
+//     (assimilator_decoder.py:195-199).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gw_b200.h"
+#include "gw_internal.h"
+#include "gw_ops.h"
+
+namespace gw {
+
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches += n; }
+
+#define GW_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      gw::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                            \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+#define GW_CHECK(cond, msg)       \
+  do {                            \
+    if (!(cond)) {                \
+      gw::set_error(msg);         \
+      return 1;                   \
+    }                             \
+  } while (0)
+#define GW_TRY(expr)        \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != 0) return _r; \
+  } while (0)
+
+struct Mlp {  // views into the plan-owned weight buffer; Linear l: W[l] [out_l, in_l], b[l] [out_l]
+  int L = 0;  // hidden layers; there are L+1 Linear layers
+  std::vector<const float*> W, b;
+  std::vector<int> in, out;
+  const float* ln_g = nullptr;
+  const float* ln_b = nullptr;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + " B): " + cudaGetErrorString(e));
+      p = nullptr;
+      n = 0;
+      return 1;
+    }
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace gw
+
+using namespace gw;
+
+struct gw_plan {
+  gw_dims d;
+  int device = 0;
+  int n_in_cur = 0;
+  // graphs
+  DevBuf<int32_t> enc_mesh, enc_perm, enc_ptr, lat_src, lat_dst, lat_ptr, dec_src, dec_ptr;
+  DevBuf<float> enc_attr, lat_attr, dec_attr;
+  bool have_enc = false, have_lat = false, have_dec = false;   // graphs uploaded
+  bool w_enc = false, w_proc = false, w_dec = false;            // weight groups bound (standalone sub-modules bind one)
+  // weights (plan-owned copy) and views
+  DevBuf<float> wbuf;
+  std::map<std::string, std::pair<const float*, std::pair<int64_t, int64_t>>> params;
+  Mlp enc_node, enc_edge_enc, enc_lat_edge_enc, enc_blk_edge, enc_blk_node;
+  Mlp dec_edge_enc, dec_blk_edge, dec_blk_node, dec_node_dec;
+  std::vector<Mlp> proc_edge, proc_node;
+  const float* h3_nodes = nullptr;  // [n_mesh, in_dim] or null (assimilator: zeros)
+  DevBuf<float> zeros_h3;
+  // weight constants
+  DevBuf<float> e_enc, xm0, C1_enc, e_lat, e_dec, E1_dec, tmpP;
+  // scratch
+  // scratch.  chunk = samples processed per pass through the encoder / decoder stages.
+  int chunk = 1;
+  DevBuf<float> bufA, bufB;   // [chunk*max_rows, max_hidden]   hidden-activation ping-pong of run_mlp
+  DevBuf<float> rows_n;       // [chunk*max(n_in,n_out), Dn]    node-encoded lat/lon rows (encoder) / updated lat/lon rows (decoder)
+  DevBuf<float> rows_e;       // [chunk*max(n_in,n_dec_edges), De]  updated edge features e' of the encoder / decoder block
+  DevBuf<float> xbuf0, xbuf1; // [max_batch*n_mesh, Dn]         mesh node state, double buffered (Jacobi update)
+  DevBuf<float> ebuf0, ebuf1; // [max_batch*n_lat_edges, De]    latent edge state, double buffered
+  DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
+  size_t total_bytes = 0;
+  // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
+  bool timing = false;
+  int cur_tag = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Stamp { int tag; cudaEvent_t a, b; };
+  std::vector<Stamp> stamps;
+};
+
+namespace gw {
+
+static RowSrc src_stream(const float* base, int ld, int width, int rows_per_sample, int col0 = 0) {
+  RowSrc s;
+  s.kind = SRC_STREAM, s.base = base, s.ld = ld, s.width = width, s.src_rows = rows_per_sample, s.col0 = col0;
+  return s;
+}
+static RowSrc src_bcast(const float* base, int ld, int width, int col0 = 0) {
+  RowSrc s;
+  s.kind = SRC_BCAST, s.base = base, s.ld = ld, s.width = width, s.col0 = col0;
+  return s;
+}
+static RowSrc src_gather(const float* base, int ld, int width, const int32_t* idx, int src_rows, int col0 = 0) {
+  RowSrc s;
+  s.kind = SRC_GATHER, s.base = base, s.ld = ld, s.width = width, s.idx = idx, s.src_rows = src_rows, s.col0 = col0;
+  return s;
+}
+static RowSrc src_bgather(const float* base, int ld, int width, const int32_t* idx) {
+  RowSrc s;
+  s.kind = SRC_BGATHER, s.base = base, s.ld = ld, s.width = width, s.idx = idx;
+  return s;
+}
+static RowSrc src_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows) {
+  RowSrc s;
+  s.kind = SRC_SEGSUM, s.base = base, s.ld = ld, s.width = width, s.ptr = ptr, s.perm = perm, s.src_rows = src_rows;
+  return s;
+}
+static RowSrc src_gather_bcast_relu(const float* base, int ld, int width, const int32_t* idx, int src_rows,
+                                    const float* base2, int ld2) {
+  RowSrc s;
+  s.kind = SRC_GATHER_BCAST_RELU, s.base = base, s.ld = ld, s.width = width, s.idx = idx, s.src_rows = src_rows;
+  s.base2 = base2, s.ld2 = ld2;
+  return s;
+}
+
+enum KernelTag { TAG_CONST = 0, TAG_ENC_GRID, TAG_ENC_MESH, TAG_PROC_P, TAG_PROC_EDGE, TAG_PROC_NODE, TAG_DEC_P, TAG_DEC_EDGE,
+                 TAG_DEC_NODE, TAG_COUNT };
+static const char* kTagNames[TAG_COUNT] = {"const", "enc_grid", "enc_mesh", "proc_p", "proc_edge", "proc_node", "dec_p",
+                                           "dec_edge", "dec_node"};
+
+static cudaEvent_t take_event(gw_plan* p) {
+  if (p->ev_used == p->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p->ev_pool.push_back(e);
+  }
+  return p->ev_pool[p->ev_used++];
+}
+struct TimedLaunch {  // RAII bracket: records an event pair on `st` around one kernel launch when timing is on
+  gw_plan* p;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  TimedLaunch(gw_plan* p_, cudaStream_t st_) : p(p_), st(st_) {
+    if (p->timing) {
+      a = take_event(p), b = take_event(p);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~TimedLaunch() {
+    if (p->timing) {
+      cudaEventRecord(b, st);
+      p->stamps.push_back({p->cur_tag, a, b});
+    }
+  }
+};
+
+static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
+  cudaError_t e;
+  {
+    TimedLaunch t(p, st);
+    e = launch_rowop_simt(op, st);
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("row-op launch failed: ") + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// Runs an MLP whose first Linear is described by `first` (A sources / addends / weight slice already set; its
+// W/K/ldw/bias may have been overridden by the caller for factored layer 1) and whose remaining layers stream
+// through the ping-pong scratch.  If `first_is_virtual`, layer 0 has already been applied by the A-assembly of
+// `first` (decoder edge MLP: relu(P[src]+E1)) and `first` describes Linear 1.
+static int run_mlp(gw_plan* p, const Mlp& m, GemmOp first, bool first_is_virtual, bool use_ln, const RowSrc& residual,
+                   float* out, int ldo, cudaStream_t st) {
+  const int rows = first.rows_per_sample, batch = first.batch;
+  float* ping = p->bufA.p;
+  float* pong = p->bufB.p;
+  const int l0 = first_is_virtual ? 1 : 0;
+  for (int l = l0; l <= m.L; ++l) {
+    GemmOp op;
+    if (l == l0) {
+      op = first;
+    } else {
+      op.rows_per_sample = rows, op.batch = batch;
+      op.a[0] = src_stream(ping, m.in[l], m.in[l], rows);
+      op.W = m.W[l], op.K = m.in[l], op.ldw = m.in[l], op.bias = m.b[l];
+    }
+    op.N = m.out[l];
+    if (l < m.L) {
+      op.relu = 1;
+      op.out = pong, op.ldo = m.out[l];
+    } else {
+      op.relu = 0;
+      if (use_ln) op.ln_gamma = m.ln_g, op.ln_beta = m.ln_b;
+      op.residual = residual;
+      op.out = out, op.ldo = ldo;
+    }
+    GW_TRY(run_op(p, op, st));
+    std::swap(ping, pong);
+  }
+  return 0;
+}
+
+static GemmOp first_op(int rows, int batch, const RowSrc& a0, const RowSrc& a1, const float* W, int K, int ldw,
+                       const float* bias) {
+  GemmOp op;
+  op.rows_per_sample = rows, op.batch = batch;
+  op.a[0] = a0, op.a[1] = a1;
+  op.W = W, op.K = K, op.ldw = ldw, op.bias = bias;
+  return op;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight lookup
+// ---------------------------------------------------------------------------------------------------------------
+static int find_param(gw_plan* p, const std::string& name, int64_t rows, int64_t cols, const float** out) {
+  auto it = p->params.find(name);
+  if (it == p->params.end()) {
+    set_error("missing parameter '" + name + "'");
+    return 1;
+  }
+  if (it->second.second.first != rows || it->second.second.second != cols) {
+    set_error("parameter '" + name + "' has shape [" + std::to_string(it->second.second.first) + "," +
+              std::to_string(it->second.second.second) + "], expected [" + std::to_string(rows) + "," +
+              std::to_string(cols) + "]");
+    return 1;
+  }
+  *out = it->second.first;
+  return 0;
+}
+
+static int bind_mlp(gw_plan* p, const std::string& prefix, int in_dim, int hidden, int out_dim, int L, bool norm, Mlp* m) {
+  m->L = L;
+  m->W.assign(L + 1, nullptr), m->b.assign(L + 1, nullptr), m->in.assign(L + 1, 0), m->out.assign(L + 1, 0);
+  int d = in_dim;
+  for (int l = 0; l <= L; ++l) {
+    int o = (l < L) ? hidden : out_dim;
+    std::string k = prefix + ".model." + std::to_string(2 * l);
+    GW_TRY(find_param(p, k + ".weight", o, d, &m->W[l]));
+    GW_TRY(find_param(p, k + ".bias", o, 1, &m->b[l]));
+    m->in[l] = d, m->out[l] = o;
+    d = o;
+  }
+  if (norm) {
+    std::string k = prefix + ".model." + std::to_string(2 * L + 1);
+    GW_TRY(find_param(p, k + ".weight", out_dim, 1, &m->ln_g));
+    GW_TRY(find_param(p, k + ".bias", out_dim, 1, &m->ln_b));
+  }
+  return 0;
+}
+
+static int bind_all(gw_plan* p) {
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, Hn = d.hidden_node, He = d.hidden_edge;
+  const int Ln = d.hidden_layers_node, Le = d.hidden_layers_edge;
+  auto has = [&](const char* k) { return p->params.count(k) != 0; };
+  p->w_enc = p->w_proc = p->w_dec = false;
+  if (has("encoder.node_encoder.model.0.weight")) {
+    GW_TRY(bind_mlp(p, "encoder.node_encoder", d.in_dim, Hn, Dn, Ln, true, &p->enc_node));
+    GW_TRY(bind_mlp(p, "encoder.edge_encoder", d.enc_edge_attr_dim, He, De, Le, true, &p->enc_edge_enc));
+    GW_TRY(bind_mlp(p, "encoder.latent_edge_encoder", 2, He, De, Le, true, &p->enc_lat_edge_enc));
+    GW_TRY(bind_mlp(p, "encoder.graph_processor.blocks.0.edge_model.edge_mlp", 2 * Dn + De, He, De, Le, true, &p->enc_blk_edge));
+    GW_TRY(bind_mlp(p, "encoder.graph_processor.blocks.0.node_model.node_mlp", Dn + De, Hn, Dn, Ln, true, &p->enc_blk_node));
+    if (has("encoder.h3_nodes")) {
+      GW_TRY(find_param(p, "encoder.h3_nodes", d.n_mesh, d.in_dim, &p->h3_nodes));
+    } else {  // AssimilatorEncoder keeps h3_nodes as a plain zero tensor (assimilator_encoder.py:80)
+      p->h3_nodes = p->zeros_h3.p;
+    }
+    p->w_enc = true;
+  }
+  if (has("processor.graph_processor.blocks.0.edge_model.edge_mlp.model.0.weight")) {
+    p->proc_edge.assign(d.num_blocks, Mlp()), p->proc_node.assign(d.num_blocks, Mlp());
+    for (int b = 0; b < d.num_blocks; ++b) {
+      std::string pre = "processor.graph_processor.blocks." + std::to_string(b);
+      GW_TRY(bind_mlp(p, pre + ".edge_model.edge_mlp", 2 * Dn + De, He, De, Le, true, &p->proc_edge[b]));
+      GW_TRY(bind_mlp(p, pre + ".node_model.node_mlp", Dn + De, Hn, Dn, Ln, true, &p->proc_node[b]));
+    }
+    p->w_proc = true;
+  }
+  if (has("decoder.edge_encoder.model.0.weight")) {
+    GW_TRY(bind_mlp(p, "decoder.edge_encoder", 2, He, De, 2, true, &p->dec_edge_enc));  // 2 hidden layers hard-coded: assimilator_decoder.py:109
+    GW_TRY(bind_mlp(p, "decoder.graph_processor.blocks.0.edge_model.edge_mlp", 2 * Dn + De, He, De, Le, true, &p->dec_blk_edge));
+    GW_TRY(bind_mlp(p, "decoder.graph_processor.blocks.0.node_model.node_mlp", Dn + De, Hn, Dn, Ln, true, &p->dec_blk_node));
+    GW_TRY(bind_mlp(p, "decoder.node_decoder", Dn, d.hidden_dec, d.out_dim, d.hidden_layers_dec, false, &p->dec_node_dec));
+    p->w_dec = true;
+  }
+  GW_CHECK(p->w_enc || p->w_proc || p->w_dec, "no encoder./processor./decoder. parameter group found in the table");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight-constant precompute
+// ---------------------------------------------------------------------------------------------------------------
+static int precompute_encoder_constants(gw_plan* p, cudaStream_t st) {
+  p->cur_tag = TAG_CONST;
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge;
+  const int N = p->n_in_cur;
+  RowSrc none;
+  // e_enc = edge_encoder(edge_attr)                                              encoder.py:206
+  {
+    const Mlp& m = p->enc_edge_enc;
+    GemmOp f = first_op(N, 1, src_stream(p->enc_attr.p, d.enc_edge_attr_dim, d.enc_edge_attr_dim, N), none, m.W[0],
+                        m.in[0], m.in[0], m.b[0]);
+    GW_TRY(run_mlp(p, m, f, false, true, none, p->e_enc.p, De, st));
+  }
+  // C1_enc[p] = W1e e_enc[p] + W1d xm0[mesh(p)] + b1                              layer 1 of graph_net_block.py:131-133
+  {
+    const Mlp& m = p->enc_blk_edge;
+    GemmOp t;  // tmpP = xm0 . W1d^T   [H, He]
+    t.rows_per_sample = d.n_mesh, t.batch = 1;
+    t.a[0] = src_stream(p->xm0.p, Dn, Dn, d.n_mesh);
+    t.W = m.W[0] + Dn, t.K = Dn, t.ldw = m.in[0], t.N = He;
+    t.out = p->tmpP.p, t.ldo = He;
+    GW_TRY(run_op(p, t, st));
+    GemmOp c;
+    c.rows_per_sample = N, c.batch = 1;
+    c.a[0] = src_stream(p->e_enc.p, De, De, N);
+    c.W = m.W[0] + 2 * Dn, c.K = De, c.ldw = m.in[0], c.N = He, c.bias = m.b[0];
+    c.add[0] = src_bgather(p->tmpP.p, He, He, p->enc_mesh.p);
+    c.out = p->C1_enc.p, c.ldo = He;
+    GW_TRY(run_op(p, c, st));
+  }
+  return 0;
+}
+
+static int precompute_constants(gw_plan* p, cudaStream_t st) {
+  p->cur_tag = TAG_CONST;
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge;
+  RowSrc none;
+  if (p->w_enc) {
+    // xm0 = node_encoder(h3_nodes)                                                encoder.py:199-205 (mesh rows)
+    const Mlp& m = p->enc_node;
+    GemmOp f = first_op(d.n_mesh, 1, src_stream(p->h3_nodes, d.in_dim, d.in_dim, d.n_mesh), none, m.W[0], m.in[0],
+                        m.in[0], m.b[0]);
+    GW_TRY(run_mlp(p, m, f, false, true, none, p->xm0.p, Dn, st));
+  }
+  if (p->w_enc && p->have_lat) {
+    // e_lat = latent_edge_encoder(edge_attr)                                      encoder.py:235-241
+    const Mlp& m = p->enc_lat_edge_enc;
+    GemmOp f = first_op(d.n_lat_edges, 1, src_stream(p->lat_attr.p, 2, 2, d.n_lat_edges), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+    GW_TRY(run_mlp(p, m, f, false, true, none, p->e_lat.p, De, st));
+  }
+  if (p->w_dec && p->have_dec) {
+    // e_dec = decoder.edge_encoder(edge_attr); E1_dec = W1e e_dec + b1            assimilator_decoder.py:175
+    const Mlp& m = p->dec_edge_enc;
+    GemmOp f = first_op(d.n_dec_edges, 1, src_stream(p->dec_attr.p, 2, 2, d.n_dec_edges), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+    GW_TRY(run_mlp(p, m, f, false, true, none, p->e_dec.p, De, st));
+    const Mlp& e = p->dec_blk_edge;
+    GemmOp c;
+    c.rows_per_sample = d.n_dec_edges, c.batch = 1;
+    c.a[0] = src_stream(p->e_dec.p, De, De, d.n_dec_edges);
+    c.W = e.W[0] + 2 * Dn, c.K = De, c.ldw = e.in[0], c.N = He, c.bias = e.b[0];
+    c.out = p->E1_dec.p, c.ldo = He;
+    GW_TRY(run_op(p, c, st));
+  }
+  if (p->w_enc && p->have_enc) GW_TRY(precompute_encoder_constants(p, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder.forward (encoder.py:197-242) for `nb` samples of `features`; writes x_out [nb*H, Dn].
+static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb, cudaStream_t st) {
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, N = p->n_in_cur, H = d.n_mesh;
+  RowSrc none;
+  for (int s0 = 0; s0 < nb; s0 += p->chunk) {
+    const int cb = std::min(p->chunk, nb - s0);
+    const float* f = features + (size_t)s0 * N * d.in_dim;
+    float* xg = p->rows_n.p;
+    float* eprime = p->rows_e.p;
+    // node_encoder on the lat/lon rows (encoder.py:205); the mesh rows are the constant xm0
+    p->cur_tag = TAG_ENC_GRID;
+    {
+      const Mlp& m = p->enc_node;
+      GemmOp fo = first_op(N, cb, src_stream(f, d.in_dim, d.in_dim, N), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+      GW_TRY(run_mlp(p, m, fo, false, true, none, xg, Dn, st));
+    }
+    // edge update e' = LN(MLP([x_src ; x_dst ; e])) + e   (graph_net_block.py:131-135); dst and e terms are in C1_enc
+    {
+      const Mlp& m = p->enc_blk_edge;
+      GemmOp fo = first_op(N, cb, src_stream(xg, Dn, Dn, N), none, m.W[0], Dn, m.in[0], nullptr);
+      fo.add[0] = src_bcast(p->C1_enc.p, He, He);
+      GW_TRY(run_mlp(p, m, fo, false, true, src_bcast(p->e_enc.p, De, De), eprime, De, st));
+    }
+    // mesh node update x' = LN(MLP([x ; sum_in e'])) + x   (graph_net_block.py:184-191), mesh rows only
+    p->cur_tag = TAG_ENC_MESH;
+    {
+      const Mlp& m = p->enc_blk_node;
+      GemmOp fo = first_op(H, cb, src_bcast(p->xm0.p, Dn, Dn),
+                           src_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N), m.W[0], m.in[0], m.in[0], m.b[0]);
+      GW_TRY(run_mlp(p, m, fo, false, true, src_bcast(p->xm0.p, Dn, Dn), x_out + (size_t)s0 * H * Dn, Dn, st));
+    }
+  }
+  return 0;
+}
+
+// Processor.forward (processor.py:123-128): num_blocks message-passing blocks.  x_in [nb*H, Dn] -> x_out [nb*H, Dn].
+// The graph (H nodes, El target-sorted edges) is shared by the nb samples.  e0 is the initial edge state:
+// broadcast (one copy for every sample: the constant e_lat of encoder.py:235-241) or per-sample [nb*El, De].
+struct ProcGraph {
+  int H, El;
+  const int32_t *src, *dst, *ptr;
+  const float* e0;
+  bool e0_broadcast;
+};
+static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, float* x_out, int nb, cudaStream_t st) {
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = g.H, El = g.El;
+  const float* x_cur = x_in;
+  float* xb[2] = {p->xbuf0.p, p->xbuf1.p};
+  float* eb[2] = {p->ebuf0.p, p->ebuf1.p};
+  const float* e_cur = nullptr;  // null: block 0 reads e0
+  for (int k = 0; k < d.num_blocks; ++k) {
+    const Mlp& me = p->proc_edge[k];
+    const Mlp& mn = p->proc_node[k];
+    // P = x [W1s ; W1d]^T   (two column slices of the edge MLP's first Linear)
+    p->cur_tag = TAG_PROC_P;
+    for (int h = 0; h < 2; ++h) {
+      GemmOp t;
+      t.rows_per_sample = H, t.batch = nb;
+      t.a[0] = src_stream(x_cur, Dn, Dn, H);
+      t.W = me.W[0] + h * Dn, t.K = Dn, t.ldw = me.in[0], t.N = He;
+      t.out = p->P.p + h * He, t.ldo = 2 * He;
+      GW_TRY(run_op(p, t, st));
+    }
+    float* e_next = eb[k & 1];
+    p->cur_tag = TAG_PROC_EDGE;
+    {
+      RowSrc e_src = e_cur ? src_stream(e_cur, De, De, El)
+                           : (g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El));
+      GemmOp fo = first_op(El, nb, e_src, RowSrc(), me.W[0] + 2 * Dn, De, me.in[0], me.b[0]);
+      fo.add[0] = src_gather(p->P.p, 2 * He, He, g.src, H, 0);
+      fo.add[1] = src_gather(p->P.p, 2 * He, He, g.dst, H, He);
+      GW_TRY(run_mlp(p, me, fo, false, true, e_src, e_next, De, st));
+    }
+    float* x_next = (k == d.num_blocks - 1) ? x_out : xb[k & 1];
+    if (x_next == x_cur) x_next = xb[(k & 1) ^ 1];  // never update in place: node and edge passes both read old x
+    p->cur_tag = TAG_PROC_NODE;
+    {
+      GemmOp fo = first_op(H, nb, src_stream(x_cur, Dn, Dn, H), src_segsum(e_next, De, De, g.ptr, nullptr, El),
+                           mn.W[0], mn.in[0], mn.in[0], mn.b[0]);
+      GW_TRY(run_mlp(p, mn, fo, false, true, src_stream(x_cur, Dn, Dn, H), x_next, Dn, st));
+    }
+    x_cur = x_next;
+    e_cur = e_next;
+  }
+  if (x_cur != x_out) GW_CUDA(cudaMemcpyAsync(x_out, x_cur, (size_t)nb * H * Dn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+static ProcGraph latent_graph_of(gw_plan* p) {
+  return ProcGraph{p->d.n_mesh, p->d.n_lat_edges, p->lat_src.p, p->lat_dst.p, p->lat_ptr.p, p->e_lat.p, true};
+}
+
+// AssimilatorDecoder.forward (assimilator_decoder.py:173-200) + Decoder residual (decoder.py:92-94).
+static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int start_ld, float* out, int nb, cudaStream_t st) {
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = d.n_mesh, Ed = d.n_dec_edges, No = d.n_out;
+  RowSrc none;
+  for (int s0 = 0; s0 < nb; s0 += p->chunk) {
+    const int cb = std::min(p->chunk, nb - s0);
+    const float* x = x_in + (size_t)s0 * H * Dn;
+    float* Pd = p->P.p;  // [cb*H, He]
+    float* eprime = p->rows_e.p;
+    float* xg = p->rows_n.p;
+    const Mlp& me = p->dec_blk_edge;
+    p->cur_tag = TAG_DEC_P;
+    {  // Pd = x W1s^T ; the dst operand (lat/lon nodes) is identically zero, assimilator_decoder.py:84,189-193
+      GemmOp t;
+      t.rows_per_sample = H, t.batch = cb;
+      t.a[0] = src_stream(x, Dn, Dn, H);
+      t.W = me.W[0], t.K = Dn, t.ldw = me.in[0], t.N = He;
+      t.out = Pd, t.ldo = He;
+      GW_TRY(run_op(p, t, st));
+    }
+    p->cur_tag = TAG_DEC_EDGE;
+    {  // edge MLP: layer 1 output = relu(Pd[src] + E1_dec) is assembled on the fly as the A operand of layer 2
+      GemmOp fo;
+      fo.rows_per_sample = Ed, fo.batch = cb;
+      fo.a[0] = src_gather_bcast_relu(Pd, He, He, p->dec_src.p, H, p->E1_dec.p, He);
+      fo.W = me.W[1], fo.K = me.in[1], fo.ldw = me.in[1], fo.bias = me.b[1];
+      GW_TRY(run_mlp(p, me, fo, true, true, src_bcast(p->e_dec.p, De, De), eprime, De, st));
+    }
+    p->cur_tag = TAG_DEC_NODE;
+    {  // lat/lon node update: cat([0 ; agg]) -> only the agg half of W1 contributes; residual x == 0
+      const Mlp& mn = p->dec_blk_node;
+      GemmOp fo = first_op(No, cb, src_segsum(eprime, De, De, p->dec_ptr.p, nullptr, Ed), none, mn.W[0] + Dn, De, mn.in[0], mn.b[0]);
+      GW_TRY(run_mlp(p, mn, fo, false, true, none, xg, Dn, st));
+    }
+    {  // node_decoder (no norm) + start-feature residual (decoder.py:93)
+      const Mlp& m = p->dec_node_dec;
+      GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+      RowSrc res;
+      if (start && d.residual_dim > 0) res = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
+      GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * d.out_dim, d.out_dim, st));
+    }
+  }
+  return 0;
+}
+
+enum { NEED_ENC = 1, NEED_PROC = 2, NEED_DEC = 4 };
+static int check_ready(gw_plan* p, int batch, int need) {
+  GW_CHECK(p != nullptr, "null plan");
+  if (need & NEED_ENC) GW_CHECK(p->have_enc && p->have_lat && p->w_enc, "encoder stage needs the encoder + latent graphs and encoder.* weights");
+  if (need & NEED_PROC) GW_CHECK(p->w_proc, "processor stage needs processor.* weights");
+  if (need & NEED_DEC) GW_CHECK(p->have_dec && p->w_dec, "decoder stage needs the decoder graph and decoder.* weights");
+  GW_CHECK(batch >= 1 && batch <= p->d.max_batch, "batch out of range [1, max_batch]");
+  GW_CUDA(cudaSetDevice(p->device));
+  return 0;
+}
+
+}  // namespace gw
+
+// ===================================================================================================================
+// C ABI
+// ===================================================================================================================
+extern "C" {
+
+int gw_abi_version(void) { return GW_ABI_VERSION; }
+const char* gw_last_error(void) { return gw::g_err.c_str(); }
+int64_t gw_launch_count(void) { return gw::g_launches; }
+void gw_launch_count_reset(void) { gw::g_launches = 0; }
+
+int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
+  GW_CHECK(dims && out_plan, "null argument");
+  const gw_dims& d = *dims;
+  GW_CHECK(d.n_in >= 0 && d.n_out >= 0 && d.n_mesh > 0 && d.n_lat_edges >= 0 && d.n_dec_edges >= 0,
+           "graph sizes must be non-negative (n_mesh positive); a standalone sub-module leaves the parts it lacks at 0");
+  GW_CHECK(d.in_dim > 0 && d.out_dim > 0 && d.node_dim > 0 && d.edge_dim > 0, "feature sizes must be positive");
+  GW_CHECK(d.hidden_layers_node >= 1 && d.hidden_layers_edge >= 1 && d.hidden_layers_dec >= 1, "hidden_layers must be >= 1");
+  GW_CHECK(d.node_dim <= 256 && d.edge_dim <= 256, "LayerNorm rows wider than 256 are not supported");
+  GW_CHECK(d.residual_dim == 0 || d.residual_dim == d.out_dim,
+           "residual_dim must equal out_dim (the reference adds start features of the same width, decoder.py:93)");
+  GW_CHECK(d.max_batch >= 1, "max_batch must be >= 1");
+  GW_CHECK(d.precision == GW_PREC_FP32_SIMT, "only GW_PREC_FP32_SIMT is built into this library version");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    gw::set_error("no CUDA device available (libgwb200 has no CPU fallback)");
+    return 1;
+  }
+  gw_plan* p = new gw_plan();
+  p->d = d;
+  GW_CUDA(cudaGetDevice(&p->device));
+  const size_t Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, Hn = d.hidden_node;
+  const size_t max_hid = std::max({Dn, De, He, Hn, (size_t)d.hidden_dec, (size_t)d.out_dim});
+  const size_t max_rows = std::max({(size_t)d.n_in, (size_t)d.n_out, (size_t)d.n_mesh, (size_t)d.n_lat_edges, (size_t)d.n_dec_edges});
+  // chunking: keep the per-pass scratch of the lat/lon-sized stages under ~48 GB
+  const size_t per_sample = (2 * max_rows * max_hid + std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De +
+                             std::max((size_t)d.n_in, (size_t)d.n_out) * Dn) * sizeof(float);
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(d.max_batch, (48ull << 30) / std::max<size_t>(per_sample, 1)));
+  p->chunk = (int)chunk;
+  const size_t B = d.max_batch;
+  int rc = 0;
+  rc |= p->enc_mesh.alloc(d.n_in) | p->enc_perm.alloc(d.n_in) | p->enc_ptr.alloc(d.n_mesh + 1);
+  rc |= p->enc_attr.alloc((size_t)d.n_in * d.enc_edge_attr_dim);
+  rc |= p->lat_src.alloc(d.n_lat_edges) | p->lat_dst.alloc(d.n_lat_edges) | p->lat_ptr.alloc(d.n_mesh + 1);
+  rc |= p->lat_attr.alloc((size_t)d.n_lat_edges * 2);
+  rc |= p->dec_src.alloc(d.n_dec_edges) | p->dec_ptr.alloc(d.n_out + 1) | p->dec_attr.alloc((size_t)d.n_dec_edges * 2);
+  rc |= p->zeros_h3.alloc((size_t)d.n_mesh * d.in_dim);
+  rc |= p->e_enc.alloc((size_t)d.n_in * De) | p->xm0.alloc((size_t)d.n_mesh * Dn) | p->C1_enc.alloc((size_t)d.n_in * He);
+  rc |= p->e_lat.alloc((size_t)d.n_lat_edges * De) | p->e_dec.alloc((size_t)d.n_dec_edges * De);
+  rc |= p->E1_dec.alloc((size_t)d.n_dec_edges * He) | p->tmpP.alloc((size_t)d.n_mesh * He);
+  rc |= p->bufA.alloc(chunk * max_rows * max_hid) | p->bufB.alloc(chunk * max_rows * max_hid);
+  // bufA/bufB are also used for full-batch processor passes over n_lat_edges rows
+  if (!rc && B * std::max((size_t)d.n_lat_edges, (size_t)d.n_mesh) > chunk * max_rows) {
+    rc |= p->bufA.alloc(B * max_rows * max_hid) | p->bufB.alloc(B * max_rows * max_hid);
+  }
+  rc |= p->rows_n.alloc(chunk * std::max((size_t)d.n_in, (size_t)d.n_out) * Dn);
+  rc |= p->rows_e.alloc(chunk * std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De);
+  rc |= p->xbuf0.alloc(B * d.n_mesh * Dn) | p->xbuf1.alloc(B * d.n_mesh * Dn);
+  rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
+  rc |= p->P.alloc(B * d.n_mesh * 2 * He);
+  if (rc) {
+    std::string keep = gw::g_err;
+    gw_plan_destroy(p);
+    gw::set_error(keep);
+    return 1;
+  }
+  GW_CUDA(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
+  p->n_in_cur = d.n_in;
+  *out_plan = p;
+  return 0;
+}
+
+int gw_plan_destroy(gw_plan* p) {
+  if (!p) return 0;
+  for (DevBuf<int32_t>* b : {&p->enc_mesh, &p->enc_perm, &p->enc_ptr, &p->lat_src, &p->lat_dst, &p->lat_ptr, &p->dec_src, &p->dec_ptr})
+    b->release();
+  for (DevBuf<float>* b : {&p->enc_attr, &p->lat_attr, &p->dec_attr, &p->wbuf, &p->zeros_h3, &p->e_enc, &p->xm0, &p->C1_enc,
+                           &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
+                           &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
+    b->release();
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  delete p;
+  return 0;
+}
+
+int64_t gw_plan_device_bytes(const gw_plan* p) {
+  if (!p) return 0;
+  size_t t = 0;
+  for (const DevBuf<int32_t>* b : {&p->enc_mesh, &p->enc_perm, &p->enc_ptr, &p->lat_src, &p->lat_dst, &p->lat_ptr, &p->dec_src, &p->dec_ptr})
+    t += b->bytes();
+  for (const DevBuf<float>* b : {&p->enc_attr, &p->lat_attr, &p->dec_attr, &p->wbuf, &p->zeros_h3, &p->e_enc, &p->xm0, &p->C1_enc,
+                                 &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e,
+                                 &p->xbuf0, &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
+    t += b->bytes();
+  return (int64_t)t;
+}
+
+int gw_plan_set_encoder_graph(gw_plan* p, int32_t n_in, const int32_t* enc_mesh, const int32_t* perm, const int32_t* ptr,
+                              const float* attr, void* stream) {
+  GW_CHECK(p && enc_mesh && perm && ptr && attr, "null argument");
+  GW_CHECK(n_in >= 1 && n_in <= p->d.n_in, "n_in exceeds the plan's capacity (gw_dims.n_in)");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  GW_CUDA(cudaMemcpyAsync(p->enc_mesh.p, enc_mesh, (size_t)n_in * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->enc_perm.p, perm, (size_t)n_in * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->enc_ptr.p, ptr, (size_t)(p->d.n_mesh + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->enc_attr.p, attr, (size_t)n_in * p->d.enc_edge_attr_dim * 4, cudaMemcpyDeviceToDevice, st));
+  p->n_in_cur = n_in;
+  p->have_enc = true;
+  if (p->w_enc) GW_TRY(gw::precompute_encoder_constants(p, st));  // per-call graphs (assimilator_encoder.py:118)
+  return 0;
+}
+
+int gw_plan_set_latent_graph(gw_plan* p, const int32_t* src, const int32_t* dst, const int32_t* ptr, const float* attr, void* stream) {
+  GW_CHECK(p && src && dst && ptr && attr, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  const size_t El = p->d.n_lat_edges;
+  GW_CUDA(cudaMemcpyAsync(p->lat_src.p, src, El * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->lat_dst.p, dst, El * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->lat_ptr.p, ptr, (size_t)(p->d.n_mesh + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->lat_attr.p, attr, El * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  p->have_lat = true;
+  p->w_enc = p->w_proc = p->w_dec = false;  // constants depend on the graphs: weights must be (re)uploaded after
+  return 0;
+}
+
+int gw_plan_set_decoder_graph(gw_plan* p, const int32_t* src, const int32_t* ptr, const float* attr, void* stream) {
+  GW_CHECK(p && src && ptr && attr, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  const size_t Ed = p->d.n_dec_edges;
+  GW_CUDA(cudaMemcpyAsync(p->dec_src.p, src, Ed * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->dec_ptr.p, ptr, (size_t)(p->d.n_out + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->dec_attr.p, attr, Ed * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  p->have_dec = true;
+  p->w_enc = p->w_proc = p->w_dec = false;
+  return 0;
+}
+
+int gw_plan_set_weights(gw_plan* p, const gw_param* params, int32_t n, void* stream) {
+  GW_CHECK(p && params && n > 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    GW_CHECK(params[i].name && params[i].data && params[i].rows > 0 && params[i].cols > 0, "malformed gw_param entry");
+    total += ((size_t)params[i].rows * params[i].cols + 63) / 64 * 64;  // 256-byte aligned slices
+  }
+  if (p->wbuf.n != total) GW_TRY(p->wbuf.alloc(total));
+  p->params.clear();
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    size_t cnt = (size_t)params[i].rows * params[i].cols;
+    GW_CUDA(cudaMemcpyAsync(p->wbuf.p + off, params[i].data, cnt * 4, cudaMemcpyDeviceToDevice, st));
+    p->params[params[i].name] = {p->wbuf.p + off, {params[i].rows, params[i].cols}};
+    off += (cnt + 63) / 64 * 64;
+  }
+  GW_TRY(gw::bind_all(p));
+  GW_TRY(gw::precompute_constants(p, st));
+  return 0;
+}
+
+int gw_encoder_forward(gw_plan* p, const float* features, float* x_out, int32_t batch, void* stream) {
+  GW_TRY(gw::check_ready(p, batch, gw::NEED_ENC));
+  GW_CHECK(features && x_out, "null argument");
+  return gw::stage_encoder(p, features, x_out, batch, (cudaStream_t)stream);
+}
+
+int gw_processor_forward(gw_plan* p, const float* x_in, float* x_out, int32_t batch, void* stream) {
+  GW_TRY(gw::check_ready(p, batch, gw::NEED_PROC));
+  GW_CHECK(x_in && x_out, "null argument");
+  GW_CHECK(p->have_lat && p->w_enc, "gw_processor_forward uses the plan's latent graph and encoded latent edges; "
+                                    "use gw_processor_forward_graph for caller-supplied graphs");
+  return gw::stage_processor(p, gw::latent_graph_of(p), x_in, x_out, batch, (cudaStream_t)stream);
+}
+
+int gw_processor_forward_graph(gw_plan* p, const float* x_in, float* x_out, const float* edge_attr, int32_t n_nodes,
+                               int32_t n_edges, const int32_t* src, const int32_t* dst, const int32_t* ptr, void* stream) {
+  GW_TRY(gw::check_ready(p, 1, gw::NEED_PROC));
+  GW_CHECK(x_in && x_out && edge_attr && src && dst && ptr, "null argument");
+  GW_CHECK(n_nodes >= 1 && (size_t)n_nodes <= (size_t)p->d.max_batch * p->d.n_mesh, "n_nodes exceeds max_batch*n_mesh");
+  GW_CHECK(n_edges >= 1 && (size_t)n_edges <= (size_t)p->d.max_batch * p->d.n_lat_edges, "n_edges exceeds max_batch*n_lat_edges");
+  gw::ProcGraph g{n_nodes, n_edges, src, dst, ptr, edge_attr, false};
+  return gw::stage_processor(p, g, x_in, x_out, 1, (cudaStream_t)stream);
+}
+
+int gw_decoder_forward(gw_plan* p, const float* x_in, const float* start, int32_t start_ld, float* out, int32_t batch, void* stream) {
+  GW_TRY(gw::check_ready(p, batch, gw::NEED_DEC));
+  GW_CHECK(x_in && out, "null argument");
+  GW_CHECK(p->d.residual_dim == 0 || (start && start_ld >= p->d.residual_dim), "start features required (decoder.py:93)");
+  return gw::stage_decoder(p, x_in, start, start_ld, out, batch, (cudaStream_t)stream);
+}
+
+int gw_forward(gw_plan* p, const float* features, float* out, int32_t batch, void* stream) {
+  GW_TRY(gw::check_ready(p, batch, gw::NEED_ENC | gw::NEED_PROC | gw::NEED_DEC));
+  GW_CHECK(features && out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  // x lives in xbuf0 between stages
+  GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, batch, st));
+  GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, batch, st));
+  return gw::stage_decoder(p, p->xbuf0.p, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, batch, st);
+}
+
+int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {
+  GW_CHECK(p && edge_attr_out, "null argument");
+  GW_CHECK(p->w_enc && p->have_lat, "needs the latent graph and encoder.* weights");
+  GW_CUDA(cudaMemcpyAsync(edge_attr_out, p->e_lat.p, p->e_lat.bytes(), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int gw_timing_enable(gw_plan* p, int32_t on) {
+  GW_CHECK(p != nullptr, "null plan");
+  p->timing = on != 0;
+  p->stamps.clear();
+  p->ev_used = 0;
+  return 0;
+}
+
+int32_t gw_timing_num_tags(void) { return gw::TAG_COUNT; }
+const char* gw_timing_tag_name(int32_t tag) { return (tag >= 0 && tag < gw::TAG_COUNT) ? gw::kTagNames[tag] : ""; }
+
+int gw_timing_read(gw_plan* p, int64_t* launches, double* ms, void* stream) {
+  GW_CHECK(p && launches && ms, "null argument");
+  GW_CUDA(cudaSetDevice(p->device));
+  GW_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int t = 0; t < gw::TAG_COUNT; ++t) launches[t] = 0, ms[t] = 0.0;
+  for (const auto& s : p->stamps) {
+    float f = 0.f;
+    GW_CUDA(cudaEventElapsedTime(&f, s.a, s.b));
+    launches[s.tag] += 1;
+    ms[s.tag] += f;
+  }
+  p->stamps.clear();
+  p->ev_used = 0;
+  return 0;
+}
+
+}  // extern "C"

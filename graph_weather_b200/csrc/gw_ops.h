@@ -1,0 +1,54 @@
+// gw_ops.h -- POD descriptors shared by the host plan and the kernels.
+//
+// Every stage of the encode-process-decode forward is a chain of "row ops":
+//     out[r, :] = residual(r) + LN( relu( A(r, :) . W^T + bias + addends(r) ) )        (each part optional)
+// over R = batch * rows_per_sample rows, where the A row and the addends are assembled on the fly from
+// "row sources" (stream / broadcast-over-batch / gather by index / CSR segment sum / relu(gather+broadcast)).
+// This is what lets the kernels skip the reference's materialised cat([x[row], x[col], e]) (graph_net_block.py:131),
+// scatter_sum output (:188) and replicated edge tensors (encoder.py:206-218).
+#pragma once
+#include <stdint.h>
+
+namespace gw {
+
+enum SrcKind : int32_t {
+  SRC_NONE = 0,
+  SRC_STREAM = 1,      // base[(b*rows + i)*ld + col0 + k]                       per-sample rows
+  SRC_BCAST = 2,       // base[i*ld + col0 + k]                                  same rows for every sample
+  SRC_GATHER = 3,      // base[(b*src_rows + idx[i])*ld + col0 + k]              per-sample table, shared index
+  SRC_SEGSUM = 4,      // sum_{j in [ptr[i],ptr[i+1])} base[(b*src_rows + eid(j))*ld + col0 + k], eid = perm ? perm[j] : j
+  SRC_GATHER_BCAST_RELU = 5,  // relu(GATHER(base, idx) + base2[i*ld2 + k])     decoder edge layer-1, see gw_api.cu
+  SRC_BGATHER = 6,     // base[idx[i]*ld + col0 + k]                             batch-invariant table, gathered
+};
+
+struct RowSrc {
+  int32_t kind = SRC_NONE;
+  int32_t width = 0;     // number of columns this source contributes
+  int32_t ld = 0;        // leading dimension of base (floats)
+  int32_t col0 = 0;      // first column inside base rows
+  const float* base = nullptr;
+  const float* base2 = nullptr;  // SRC_GATHER_BCAST_RELU: broadcast table
+  int32_t ld2 = 0;
+  int32_t src_rows = 0;  // rows per sample of the gathered / summed table
+  const int32_t* idx = nullptr;   // [rows_per_sample]
+  const int32_t* ptr = nullptr;   // [rows_per_sample+1]
+  const int32_t* perm = nullptr;  // optional edge permutation for SEGSUM
+};
+
+struct GemmOp {
+  int32_t rows_per_sample = 0;
+  int32_t batch = 0;
+  RowSrc a[2];                 // A row = concat(a[0], a[1]); K = a[0].width + a[1].width
+  const float* W = nullptr;    // [N, ldw] row-major (nn.Linear weight, possibly a column slice: pointer offset + ldw)
+  int32_t K = 0, N = 0, ldw = 0;
+  const float* bias = nullptr; // [N]
+  RowSrc add[3];               // epilogue addends, each N wide
+  int32_t relu = 0;
+  const float* ln_gamma = nullptr;  // LayerNorm over the N outputs (eps 1e-5) if non-null
+  const float* ln_beta = nullptr;
+  RowSrc residual;             // added after LN
+  float* out = nullptr;        // out[(b*rows + i)*ldo + n]
+  int32_t ldo = 0;
+};
+
+}  // namespace gw

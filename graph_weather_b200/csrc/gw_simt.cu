@@ -1,0 +1,179 @@
+// gw_simt.cu -- exact-fp32 row-op kernel on the CUDA cores (precision GW_PREC_FP32_SIMT).
+//
+// One kernel executes any gw::GemmOp: it assembles A rows from their row sources while staging them to shared
+// memory (so the reference's cat / gather / scatter_sum intermediates never exist in HBM), runs an fp32 FFMA
+// tile GEMM, and applies bias + gathered addends + ReLU + LayerNorm + residual in registers before one coalesced
+// store.  It serves (a) every op of the forward when hidden sizes are not the 256 the tcgen05 kernel is built for,
+// (b) the one-off weight-constant precompute, and (c) as the on-device fp32 cross-check of the tensor-core path.
+//
+// Tile: 64 rows x 256 cols per CTA (so a LayerNorm row never leaves the CTA), BK = 16, 256 threads; each thread
+// owns 8 rows x 8 cols (cols strided by 32 so smem reads are conflict-free and global stores coalesce); a warp
+// owns 8 complete rows, so LayerNorm statistics are 5 shuffles.
+#include <cuda_runtime.h>
+
+#include "gw_ops.h"
+#include "gw_internal.h"
+
+namespace gw {
+
+constexpr int BM = 64, BN = 256, BK = 16, NT = 256;
+
+__device__ __forceinline__ float fetch_src(const RowSrc& s, int b, int i, int k) {
+  switch (s.kind) {
+    case SRC_STREAM:
+      return __ldg(s.base + ((size_t)b * s.src_rows + i) * s.ld + s.col0 + k);
+    case SRC_BCAST:
+      return __ldg(s.base + (size_t)i * s.ld + s.col0 + k);
+    case SRC_GATHER:
+      return __ldg(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld + s.col0 + k);
+    case SRC_BGATHER:
+      return __ldg(s.base + (size_t)__ldg(s.idx + i) * s.ld + s.col0 + k);
+    case SRC_SEGSUM: {
+      int j0 = __ldg(s.ptr + i), j1 = __ldg(s.ptr + i + 1);
+      float acc = 0.f;
+      for (int j = j0; j < j1; ++j) {  // same left-to-right order as scatter_add over the reference edge list
+        int e = s.perm ? __ldg(s.perm + j) : j;
+        acc += __ldg(s.base + ((size_t)b * s.src_rows + e) * s.ld + s.col0 + k);
+      }
+      return acc;
+    }
+    case SRC_GATHER_BCAST_RELU: {
+      float v = __ldg(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld + s.col0 + k) +
+                __ldg(s.base2 + (size_t)i * s.ld2 + k);
+      return fmaxf(v, 0.f);
+    }
+    default:
+      return 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(NT) gw_rowop_f32_kernel(const GemmOp op) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 1];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int R = op.rows_per_sample * op.batch;
+  const int row0 = blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  const int K = op.K, N = op.N;
+  const int k_split = op.a[0].width;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A tile: 64 x 16, element e -> (row e/16, k e%16): 16 consecutive lanes read 16 consecutive k of one row
+#pragma unroll
+    for (int it = 0; it < (BM * BK) / NT; ++it) {
+      int e = tid + it * NT;
+      int r = e / BK, kk = e % BK;
+      int gr = row0 + r, gk = k0 + kk;
+      float v = 0.f;
+      if (gr < R && gk < K) {
+        int b = gr / op.rows_per_sample, i = gr - b * op.rows_per_sample;
+        v = (gk < k_split) ? fetch_src(op.a[0], b, i, gk) : fetch_src(op.a[1], b, i, gk - k_split);
+      }
+      As[kk][r] = v;
+    }
+    // W tile: 256 x 16 from W[n, k] (k contiguous)
+#pragma unroll
+    for (int it = 0; it < (BN * BK) / NT; ++it) {
+      int e = tid + it * NT;
+      int n = e / BK, kk = e % BK;
+      int gn = col0 + n, gk = k0 + kk;
+      Ws[kk][n] = (gn < N && gk < K) ? __ldg(op.W + (size_t)gn * op.ldw + gk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = Ws[kk][tx + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gr = row0 + ty * 8 + i;
+    const bool row_ok = gr < R;  // warp-uniform
+    int b = 0, li = 0;
+    if (row_ok) {
+      b = gr / op.rows_per_sample;
+      li = gr - b * op.rows_per_sample;
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int gn = col0 + tx + 32 * j;
+      float x = acc[i][j];
+      if (row_ok && gn < N) {
+        if (op.bias) x += __ldg(op.bias + gn);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+          if (op.add[s].kind != SRC_NONE) x += fetch_src(op.add[s], b, li, gn);
+        if (op.relu) x = fmaxf(x, 0.f);
+      } else {
+        x = 0.f;
+      }
+      v[j] = x;
+    }
+    if (op.ln_gamma) {  // LayerNorm over N (<= 256, one CTA column block), eps = 1e-5, biased variance (torch)
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)N;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int gn = col0 + tx + 32 * j;
+        float d = (gn < N) ? v[j] - mean : 0.f;
+        q += d * d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.0f / sqrtf(q / (float)N + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int gn = col0 + tx + 32 * j;
+        if (gn < N) v[j] = (v[j] - mean) * rstd * __ldg(op.ln_gamma + gn) + __ldg(op.ln_beta + gn);
+      }
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int gn = col0 + tx + 32 * j;
+        if (gn < N) {
+          float x = v[j];
+          if (op.residual.kind != SRC_NONE) x += fetch_src(op.residual, b, li, gn);
+          op.out[(size_t)gr * op.ldo + gn] = x;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream) {
+  const long long R = (long long)op.rows_per_sample * op.batch;
+  if (R <= 0 || op.N <= 0) return cudaSuccess;
+  if (op.ln_gamma && op.N > BN) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)((op.N + BN - 1) / BN));
+  gw_rowop_f32_kernel<<<grid, NT, 0, stream>>>(op);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gw

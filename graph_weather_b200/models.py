@@ -1,0 +1,625 @@
+"""Drop-in host-side mirror of the reference's module API for the encode-process-decode path.
+
+Same class names, constructor arguments, attribute names and state_dict keys as
+    graph_weather/models/forecast.py:61-247           GraphWeatherForecaster
+    graph_weather/models/analysis.py:52-150           GraphWeatherAssimilator
+    graph_weather/models/layers/encoder.py:36-268     Encoder
+    graph_weather/models/layers/processor.py:17-128   Processor
+    graph_weather/models/layers/decoder.py:24-94      Decoder
+    graph_weather/models/layers/assimilator_{encoder,decoder}.py
+    graph_weather/models/layers/graph_net_block.py    MLP / EdgeProcessor / NodeProcessor / GraphProcessor
+so `load_state_dict` / `from_pretrained` round-trip with the reference, and sub-modules are constructed in the
+reference's order so that `torch.manual_seed(s)` gives the same initial weights.
+
+These modules hold parameters and graphs only.  Every forward goes through libgwb200.so (graph_weather_b200._capi);
+there is no eager-PyTorch or CPU execution path -- CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _capi, graphs, h3lite
+
+try:  # the reference mixes this into both wrappers (forecast.py:61, analysis.py:52)
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+
+def _no_host_path(what):
+    raise RuntimeError(
+        f"{what}: graph_weather_b200 executes only through its CUDA library on a CUDA device; "
+        "there is no CPU / eager fallback. Move the module and inputs to the GPU."
+    )
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers (graph_net_block.py)
+# ---------------------------------------------------------------------------------------------------------------
+class MLP(nn.Module):
+    """Parameter container with the reference layout (graph_net_block.py:45-61): `model.{0,2,..}` Linear, last index LayerNorm."""
+
+    def __init__(self, in_dim, out_dim=128, hidden_dim=128, hidden_layers=2, norm_type: Optional[str] = "LayerNorm",
+                 use_checkpointing: bool = False):  # fmt: skip
+        super().__init__()
+        self.use_checkpointing = use_checkpointing
+        layers = [nn.Linear(in_dim, hidden_dim), nn.ReLU()]
+        for _ in range(hidden_layers - 1):
+            layers += [nn.Linear(hidden_dim, hidden_dim), nn.ReLU()]
+        layers.append(nn.Linear(hidden_dim, out_dim))
+        if norm_type is not None:
+            assert norm_type in ["LayerNorm", "GraphNorm", "InstanceNorm", "BatchNorm", "MessageNorm"]
+            if norm_type != "LayerNorm":  # only LayerNorm resolves in the reference too (getattr(nn, ...), :58)
+                raise NotImplementedError(f"norm_type={norm_type!r}: only 'LayerNorm' is supported on the B200 path")
+            layers.append(nn.LayerNorm(out_dim))
+        self.model = nn.Sequential(*layers)
+        self.in_dim, self.out_dim, self.hidden_dim, self.hidden_layers = in_dim, out_dim, hidden_dim, hidden_layers
+
+    def forward(self, x):
+        _no_host_path("MLP.forward")
+
+
+class EdgeProcessor(nn.Module):
+    def __init__(self, in_dim_node=128, in_dim_edge=128, hidden_dim=128, hidden_layers=2, norm_type="LayerNorm"):
+        super().__init__()
+        self.edge_mlp = MLP(2 * in_dim_node + in_dim_edge, in_dim_edge, hidden_dim, hidden_layers, norm_type)
+
+
+class NodeProcessor(nn.Module):
+    def __init__(self, in_dim_node=128, in_dim_edge=128, hidden_dim=128, hidden_layers=2, norm_type="LayerNorm"):
+        super().__init__()
+        self.node_mlp = MLP(in_dim_node + in_dim_edge, in_dim_node, hidden_dim, hidden_layers, norm_type)
+
+
+class _MetaBlock(nn.Module):
+    """Stands where the reference puts torch_geometric.nn.MetaLayer (graph_net_block.py:221-228): same child names."""
+
+    def __init__(self, edge_model, node_model):
+        super().__init__()
+        self.edge_model = edge_model
+        self.node_model = node_model
+
+
+class GraphProcessor(nn.Module):
+    def __init__(self, mp_iterations=15, in_dim_node=128, in_dim_edge=128, hidden_dim_node=128, hidden_dim_edge=128,
+                 hidden_layers_node=2, hidden_layers_edge=2, norm_type="LayerNorm", use_checkpointing=False):  # fmt: skip
+        super().__init__()
+        if norm_type != "LayerNorm":
+            raise NotImplementedError("the B200 message-passing kernels implement LayerNorm MLPs (the reference default)")
+        self.use_checkpointing = use_checkpointing
+        self.blocks = nn.ModuleList()
+        for _ in range(mp_iterations):
+            self.blocks.append(
+                _MetaBlock(
+                    EdgeProcessor(in_dim_node, in_dim_edge, hidden_dim_edge, hidden_layers_edge, norm_type),
+                    NodeProcessor(in_dim_node, in_dim_edge, hidden_dim_node, hidden_layers_node, norm_type),
+                )
+            )
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# engine: one gw_plan + upload bookkeeping
+# ---------------------------------------------------------------------------------------------------------------
+def _params_fingerprint(named):
+    return tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in named)
+
+
+class _Engine:
+    """Creates the plan lazily on the device of the first input, uploads graphs once and weights whenever a parameter
+    changed (in-place optimiser steps and load_state_dict bump tensor versions; .to() changes data pointers)."""
+
+    def __init__(self, dims: dict, precision: str):
+        self.dims = dict(dims)
+        self.precision = precision
+        self.plan: Optional[_capi.Plan] = None
+        self.graph_uploaders = []  # callables(plan)
+        self._wfp = None
+
+    def _create(self, device, max_batch):
+        if self.plan is not None:
+            self.plan.close()
+        d = dict(self.dims)
+        d["max_batch"] = int(max_batch)
+        d["precision"] = _capi.PRECISIONS[self.precision]
+        self.plan = _capi.Plan(device, **d)
+        for up in self.graph_uploaders:
+            up(self.plan)
+        self._wfp = None
+
+    def ensure(self, device, batch, named_params, grow: Optional[dict] = None):
+        device = torch.device(device)
+        if device.type != "cuda":
+            _no_host_path("forward on a CPU tensor")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        need_new = self.plan is None or self.plan.device != device
+        if grow:
+            for k, v in grow.items():
+                if v > self.dims.get(k, 0):
+                    self.dims[k] = int(v)
+                    need_new = True
+        if not need_new and batch > self.plan.dims.max_batch:
+            need_new = True
+        if need_new:
+            self._create(device, max(batch, self.plan.dims.max_batch if self.plan is not None else 1))
+        named = list(named_params)
+        fp = _params_fingerprint(named)
+        if fp != self._wfp:
+            self.plan.set_weights(named)
+            self._wfp = fp
+        return self.plan
+
+    def invalidate_weights(self):
+        self._wfp = None
+
+
+def _prefixed(prefix, module):
+    return [(f"{prefix}.{k}", v) for k, v in module.state_dict(keep_vars=True).items() if torch.is_tensor(v)]
+
+
+def _latlon_list(lat_lons):
+    return [(float(p[0]), float(p[1])) for p in lat_lons]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Encoder (encoder.py)
+# ---------------------------------------------------------------------------------------------------------------
+class Encoder(nn.Module):
+    def __init__(self, lat_lons: list, resolution: int = 2, input_dim: int = 78, output_dim: int = 256, output_edge_dim: int = 256,
+                 hidden_dim_processor_node=256, hidden_dim_processor_edge=256, hidden_layers_processor_node=2,
+                 hidden_layers_processor_edge=2, mlp_norm_type="LayerNorm", use_checkpointing: bool = False,
+                 efficient_batching: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        self.use_checkpointing = use_checkpointing  # accepted for API parity; forward-only path keeps no activations
+        self.efficient_batching = efficient_batching
+        self.output_dim = output_dim
+        self.num_latlons = len(lat_lons)
+        self.resolution = resolution
+        self._g_enc = graphs.build_encoder_graph(lat_lons, resolution)
+        self._g_lat = graphs.build_mesh_graph(resolution)
+        self.num_h3 = self._g_lat.num_h3
+        self.h3_nodes = nn.Parameter(torch.zeros((h3lite.get_num_cells(resolution), input_dim), dtype=torch.float))
+        self.node_encoder = MLP(input_dim, output_dim, hidden_dim_processor_node, hidden_layers_processor_node, mlp_norm_type)
+        self.edge_encoder = MLP(2, output_edge_dim, hidden_dim_processor_edge, hidden_layers_processor_edge, mlp_norm_type)
+        self.latent_edge_encoder = MLP(2, output_edge_dim, hidden_dim_processor_edge, hidden_layers_processor_edge, mlp_norm_type)
+        self.graph_processor = GraphProcessor(1, output_dim, output_edge_dim, hidden_dim_processor_node, hidden_dim_processor_edge,
+                                              hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type)  # fmt: skip
+        self._dims = dict(
+            n_in=self.num_latlons, n_out=0, n_mesh=self.num_h3, n_lat_edges=self._g_lat.edge_index.shape[1], n_dec_edges=0,
+            in_dim=input_dim, enc_edge_attr_dim=2, out_dim=1, residual_dim=0, node_dim=output_dim, edge_dim=output_edge_dim,
+            hidden_node=hidden_dim_processor_node, hidden_edge=hidden_dim_processor_edge,
+            hidden_layers_node=hidden_layers_processor_node, hidden_layers_edge=hidden_layers_processor_edge,
+            hidden_dec=1, hidden_layers_dec=1, num_blocks=1,
+        )  # fmt: skip
+        self._engine = None
+        self._precision = precision
+        self._lat_edge_index_t = {}
+
+    # graph uploads shared with the wrappers
+    def _upload_graphs(self, plan):
+        g, m = self._g_enc, self._g_lat
+        plan.set_encoder_graph(g.mesh_local, g.perm, g.ptr, g.edge_attr)
+        plan.set_latent_graph(m.src, m.dst, m.ptr, m.edge_attr[m.perm])
+
+    def _own_engine(self):
+        if self._engine is None:
+            self._engine = _Engine(self._dims, self._precision)
+            self._engine.graph_uploaders.append(self._upload_graphs)
+        return self._engine
+
+    def _latent_outputs(self, plan, batch, device):
+        """(edge_index [2,B*El] int64, edge_attr [B*El,De]) in the reference's order and replication (encoder.py:224-242)."""
+        m = self._g_lat
+        El = m.edge_index.shape[1]
+        key = (str(device), batch)
+        if key not in self._lat_edge_index_t:
+            ei = graphs.replicate_edge_index(m.edge_index, batch) if not self.efficient_batching else m.edge_index
+            self._lat_edge_index_t = {key: torch.from_numpy(ei).to(device)}
+        sorted_attr = torch.empty((El, self._dims["edge_dim"]), dtype=torch.float32, device=device)
+        plan.latent_edge_features(sorted_attr)
+        ref_attr = torch.empty_like(sorted_attr)
+        ref_attr[torch.from_numpy(m.perm).to(device)] = sorted_attr
+        if not self.efficient_batching:
+            ref_attr = ref_attr.repeat(batch, 1)
+        return self._lat_edge_index_t[key], ref_attr
+
+    def forward(self, features: torch.Tensor):
+        if features.device.type != "cuda":
+            _no_host_path("Encoder.forward")
+        B = features.shape[0]
+        plan = self._own_engine().ensure(features.device, B, _prefixed("encoder", self))
+        f = features.detach().to(torch.float32).contiguous()
+        x = torch.empty((B * self.num_h3, self.output_dim), dtype=torch.float32, device=f.device)
+        plan.encoder_forward(f, x)
+        ei, ea = self._latent_outputs(plan, B, f.device)
+        return x, ei, ea
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Processor (processor.py)
+# ---------------------------------------------------------------------------------------------------------------
+class Processor(nn.Module):
+    def __init__(self, input_dim: int = 256, edge_dim: int = 256, num_blocks: int = 9, hidden_dim_processor_node: int = 256,
+                 hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
+                 mlp_norm_type: str = "LayerNorm", use_thermalizer: bool = False, use_checkpointing: bool = False,
+                 precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        if use_thermalizer:
+            raise NotImplementedError("use_thermalizer=True: the stochastic ThermalizerLayer is outside the accelerated path")
+        self.input_dim = input_dim
+        self.use_thermalizer = use_thermalizer
+        self.checkpoint_segments = 0
+        self.graph_processor = GraphProcessor(num_blocks, input_dim, edge_dim, hidden_dim_processor_node, hidden_dim_processor_edge,
+                                              hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type,
+                                              use_checkpointing)  # fmt: skip
+        self._cfg = dict(node_dim=input_dim, edge_dim=edge_dim, hidden_node=hidden_dim_processor_node,
+                         hidden_edge=hidden_dim_processor_edge, hidden_layers_node=hidden_layers_processor_node,
+                         hidden_layers_edge=hidden_layers_processor_edge, num_blocks=num_blocks)  # fmt: skip
+        self._precision = precision
+        self._engine = None
+        self._graph_cache = None
+
+    def set_checkpoint_segments(self, checkpoint_segments: int):
+        self.checkpoint_segments = checkpoint_segments
+
+    def _sorted_graph(self, edge_index, n_nodes):
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n_nodes)
+        if self._graph_cache is None or self._graph_cache[0] != key:
+            dst_sorted, order = torch.sort(edge_index[1], stable=True)
+            src = edge_index[0][order].to(torch.int32).contiguous()
+            ptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=edge_index.device)
+            ptr[1:] = torch.cumsum(torch.bincount(dst_sorted, minlength=n_nodes), 0).to(torch.int32)
+            self._graph_cache = (key, src, dst_sorted.to(torch.int32).contiguous(), ptr, order)
+        return self._graph_cache[1:]
+
+    def forward(self, x: torch.Tensor, edge_index, edge_attr, t: int = 0, batch_size: int = None, efficient_batching: bool = False):
+        if x.device.type != "cuda":
+            _no_host_path("Processor.forward")
+        x = x.detach().to(torch.float32).contiguous()
+        n_nodes = x.shape[0]
+        if efficient_batching and batch_size is not None and batch_size > 1:
+            # shared graph, per-sample loop in the reference (processor.py:106-122) == block-diagonal replication
+            per = n_nodes // batch_size
+            edge_index = torch.cat([edge_index + i * per for i in range(batch_size)], dim=1)
+            edge_attr = edge_attr.repeat(batch_size, 1)
+        src, dst, ptr, order = self._sorted_graph(edge_index, n_nodes)
+        ea = edge_attr.detach().to(torch.float32)[order].contiguous()
+        if self._engine is None:
+            dims = dict(n_in=0, n_out=0, n_mesh=n_nodes, n_lat_edges=int(src.numel()), n_dec_edges=0, in_dim=1,
+                        enc_edge_attr_dim=2, out_dim=1, residual_dim=0, hidden_dec=1, hidden_layers_dec=1, **self._cfg)  # fmt: skip
+            self._engine = _Engine(dims, self._precision)
+        plan = self._engine.ensure(x.device, 1, _prefixed("processor", self), grow=dict(n_mesh=n_nodes, n_lat_edges=int(src.numel())))
+        out = torch.empty_like(x)
+        plan.processor_forward_graph(x, out, ea, src, dst, ptr)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Decoders (assimilator_decoder.py, decoder.py)
+# ---------------------------------------------------------------------------------------------------------------
+class AssimilatorDecoder(nn.Module):
+    def __init__(self, lat_lons: list, resolution: int = 2, input_dim: int = 256, output_dim: int = 78, output_edge_dim: int = 256,
+                 hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
+                 hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", hidden_dim_decoder: int = 128,
+                 hidden_layers_decoder: int = 2, use_checkpointing: bool = False, efficient_batching: bool = False,
+                 precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        self.use_checkpointing = use_checkpointing
+        self.efficient_batching = efficient_batching
+        self.num_latlons = len(lat_lons)
+        self.resolution = resolution
+        self._g_dec = graphs.build_decoder_graph(lat_lons, resolution)
+        self.num_h3 = self._g_dec.num_h3
+        self.output_dim = output_dim
+        self.edge_encoder = MLP(2, output_edge_dim, hidden_dim_processor_edge, 2, mlp_norm_type)
+        self.graph_processor = GraphProcessor(1, input_dim, output_edge_dim, hidden_dim_processor_node, hidden_dim_processor_edge,
+                                              hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type)  # fmt: skip
+        self.node_decoder = MLP(input_dim, output_dim, hidden_dim_decoder, hidden_layers_decoder, None)
+        self._residual = False
+        self._dims = dict(
+            n_in=0, n_out=self.num_latlons, n_mesh=self.num_h3, n_lat_edges=0, n_dec_edges=int(self._g_dec.src.size),
+            in_dim=1, enc_edge_attr_dim=2, out_dim=output_dim, residual_dim=0, node_dim=input_dim, edge_dim=output_edge_dim,
+            hidden_node=hidden_dim_processor_node, hidden_edge=hidden_dim_processor_edge,
+            hidden_layers_node=hidden_layers_processor_node, hidden_layers_edge=hidden_layers_processor_edge,
+            hidden_dec=hidden_dim_decoder, hidden_layers_dec=hidden_layers_decoder, num_blocks=1,
+        )  # fmt: skip
+        self._precision = precision
+        self._engine = None
+
+    def _upload_graphs(self, plan):
+        g = self._g_dec
+        plan.set_decoder_graph(g.src, g.ptr, g.edge_attr)
+
+    def _own_engine(self):
+        if self._engine is None:
+            dims = dict(self._dims)
+            dims["residual_dim"] = self.output_dim if self._residual else 0
+            self._engine = _Engine(dims, self._precision)
+            self._engine.graph_uploaders.append(self._upload_graphs)
+        return self._engine
+
+    def _run(self, processor_features, batch_size, start):
+        if processor_features.device.type != "cuda":
+            _no_host_path("Decoder.forward")
+        x = processor_features.detach().to(torch.float32).contiguous()
+        plan = self._own_engine().ensure(x.device, batch_size, _prefixed("decoder", self))
+        out = torch.empty((batch_size, self.num_latlons, self.output_dim), dtype=torch.float32, device=x.device)
+        plan.decoder_forward(x, start, out, batch_size)
+        return out
+
+    def forward(self, processor_features: torch.Tensor, batch_size: int) -> torch.Tensor:
+        return self._run(processor_features, batch_size, None)
+
+
+class Decoder(AssimilatorDecoder):
+    def __init__(self, lat_lons, resolution: int = 2, input_dim: int = 256, output_dim: int = 78, output_edge_dim: int = 256,
+                 hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
+                 hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", hidden_dim_decoder: int = 128,
+                 hidden_layers_decoder: int = 2, use_checkpointing: bool = False, efficient_batching: bool = False,
+                 precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__(lat_lons, resolution, input_dim, output_dim, output_edge_dim, hidden_dim_processor_node,
+                         hidden_dim_processor_edge, hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type,
+                         hidden_dim_decoder, hidden_layers_decoder, use_checkpointing, efficient_batching, precision)  # fmt: skip
+        self._residual = True
+
+    def forward(self, processor_features: torch.Tensor, start_features: torch.Tensor, t: int = 0) -> torch.Tensor:
+        if start_features.shape[-1] != self.output_dim:  # same failure point as the reference's broadcast add (decoder.py:93)
+            raise RuntimeError(
+                f"The size of tensor a ({self.output_dim}) must match the size of tensor b ({start_features.shape[-1]}) "
+                "at non-singleton dimension 2"
+            )
+        start = start_features.detach().to(torch.float32).contiguous()
+        return self._run(processor_features, start_features.shape[0], start)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AssimilatorEncoder (assimilator_encoder.py)
+# ---------------------------------------------------------------------------------------------------------------
+class AssimilatorEncoder(nn.Module):
+    def __init__(self, resolution: int = 2, input_dim: int = 2, output_dim: int = 256, output_edge_dim: int = 256,
+                 hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
+                 hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", use_checkpointing: bool = False,
+                 precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        self.use_checkpointing = use_checkpointing
+        self.output_dim = output_dim
+        self.input_dim = input_dim
+        self.resolution = resolution
+        self._g_lat = graphs.build_mesh_graph(resolution)
+        self.num_h3 = self._g_lat.num_h3
+        self.h3_nodes = torch.zeros((h3lite.get_num_cells(resolution), input_dim), dtype=torch.float)  # plain tensor, :80
+        self.node_encoder = MLP(input_dim, output_dim, hidden_dim_processor_node, hidden_layers_processor_node, mlp_norm_type)
+        self.edge_encoder = MLP(3, output_edge_dim, hidden_dim_processor_edge, hidden_layers_processor_edge, mlp_norm_type)
+        self.latent_edge_encoder = MLP(2, output_edge_dim, hidden_dim_processor_edge, hidden_layers_processor_edge, mlp_norm_type)
+        self.graph_processor = GraphProcessor(1, output_dim, output_edge_dim, hidden_dim_processor_node, hidden_dim_processor_edge,
+                                              hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type)  # fmt: skip
+        self._dims = dict(
+            n_in=1, n_out=0, n_mesh=self.num_h3, n_lat_edges=self._g_lat.edge_index.shape[1], n_dec_edges=0, in_dim=input_dim,
+            enc_edge_attr_dim=3, out_dim=1, residual_dim=0, node_dim=output_dim, edge_dim=output_edge_dim,
+            hidden_node=hidden_dim_processor_node, hidden_edge=hidden_dim_processor_edge,
+            hidden_layers_node=hidden_layers_processor_node, hidden_layers_edge=hidden_layers_processor_edge,
+            hidden_dec=1, hidden_layers_dec=1, num_blocks=1,
+        )  # fmt: skip
+        self._precision = precision
+        self._engine = None
+        self.efficient_batching = False
+        self._obs_key = None
+        self._lat_edge_index_t = {}
+
+    def _upload_graphs(self, plan):
+        m = self._g_lat
+        plan.set_latent_graph(m.src, m.dst, m.ptr, m.edge_attr[m.perm])
+
+    def _input_graph(self, lat_lon_heights):
+        """create_input_graph (assimilator_encoder.py:170-216), rebuilt when the observation set changes."""
+        llh = lat_lon_heights.detach().cpu().numpy().astype(np.float64)
+        return graphs.build_encoder_graph(llh[:, :2], self.resolution, heights=llh[:, 2])
+
+    def _upload_obs(self, plan, lat_lon_heights):
+        key = (lat_lon_heights.data_ptr(), lat_lon_heights._version, tuple(lat_lon_heights.shape), plan.handle.value)
+        if key != self._obs_key:
+            g = self._input_graph(lat_lon_heights)
+            plan.set_encoder_graph(g.mesh_local, g.perm, g.ptr, g.edge_attr)
+            self._obs_key = key
+
+    def _own_engine(self):
+        if self._engine is None:
+            self._engine = _Engine(self._dims, self._precision)
+            self._engine.graph_uploaders.append(self._upload_graphs)
+        return self._engine
+
+    _latent_outputs = Encoder._latent_outputs
+
+    def forward(self, features: torch.Tensor, lat_lon_heights: torch.Tensor):
+        if features.device.type != "cuda":
+            _no_host_path("AssimilatorEncoder.forward")
+        B, nobs = features.shape[0], lat_lon_heights.shape[0]
+        eng = self._own_engine()
+        plan = eng.ensure(features.device, B, _prefixed("encoder", self), grow=dict(n_in=nobs))
+        self._upload_obs(plan, lat_lon_heights)
+        f = features.detach().to(torch.float32).contiguous()
+        x = torch.empty((B * self.num_h3, self.output_dim), dtype=torch.float32, device=f.device)
+        plan.encoder_forward(f, x)
+        ei, ea = self._latent_outputs(plan, B, f.device)
+        return x, ei, ea
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wrappers (forecast.py, analysis.py)
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class GraphWeatherForecasterConfig:
+    """forecast.py:14-58"""
+
+    lat_lons: list
+    resolution: int = 2
+    feature_dim: int = 78
+    aux_dim: int = 24
+    output_dim: Optional[int] = None
+    node_dim: int = 256
+    edge_dim: int = 256
+    num_blocks: int = 9
+    hidden_dim_processor_node: int = 256
+    hidden_dim_processor_edge: int = 256
+    hidden_layers_processor_node: int = 2
+    hidden_layers_processor_edge: int = 2
+    hidden_dim_decoder: int = 128
+    hidden_layers_decoder: int = 2
+    norm_type: str = "LayerNorm"
+    use_checkpointing: bool = False
+    constraint_type: str = "none"
+    use_thermalizer: bool = False
+
+    def build(self) -> "GraphWeatherForecaster":
+        return GraphWeatherForecaster(**self.__dict__)
+
+
+class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
+    """GraphWeatherForecaster(lat_lons)(features): forecast.py:61-247 (constraint_type='none', no thermalizer)."""
+
+    def __init__(self, lat_lons: list, resolution: int = 2, feature_dim: int = 78, aux_dim: int = 24, output_dim: Optional[int] = None,
+                 node_dim: int = 256, edge_dim: int = 256, num_blocks: int = 9, hidden_dim_processor_node: int = 256,
+                 hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
+                 hidden_dim_decoder: int = 128, hidden_layers_decoder: int = 2, norm_type: str = "LayerNorm",
+                 use_checkpointing: bool = False, constraint_type: str = "none", use_thermalizer: bool = False,
+                 precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        if constraint_type != "none":
+            raise NotImplementedError("constraint_type != 'none' (PhysicalConstraintLayer) is not on the accelerated path yet")
+        if use_thermalizer:
+            raise NotImplementedError("use_thermalizer=True is outside the accelerated path (stochastic layer)")
+        lat_lons = _latlon_list(lat_lons)
+        graphs.validate_lat_lons(lat_lons)
+        self.feature_dim = feature_dim
+        self.constraint_type = constraint_type
+        self.use_thermalizer = use_thermalizer
+        if output_dim is None:
+            output_dim = self.feature_dim
+        self.output_dim = output_dim
+        unique_lats = sorted(set(lat for lat, _ in lat_lons))
+        unique_lons = sorted(set(lon for _, lon in lat_lons))
+        self.grid_shape = (len(unique_lats), len(unique_lons))
+        self.original_lat_lons = list(lat_lons)
+        self.precision = precision
+        self.encoder = Encoder(lat_lons=lat_lons, resolution=resolution, input_dim=feature_dim + aux_dim, output_dim=node_dim,
+                               output_edge_dim=edge_dim, hidden_dim_processor_edge=hidden_dim_processor_edge,
+                               hidden_layers_processor_node=hidden_layers_processor_node,
+                               hidden_dim_processor_node=hidden_dim_processor_node,
+                               hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                               use_checkpointing=use_checkpointing, precision=precision)  # fmt: skip
+        self.processor = Processor(input_dim=node_dim, edge_dim=edge_dim, num_blocks=num_blocks,
+                                   hidden_dim_processor_edge=hidden_dim_processor_edge,
+                                   hidden_layers_processor_node=hidden_layers_processor_node,
+                                   hidden_dim_processor_node=hidden_dim_processor_node,
+                                   hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                                   use_thermalizer=use_thermalizer, precision=precision)  # fmt: skip
+        self.decoder = Decoder(lat_lons=lat_lons, resolution=resolution, input_dim=node_dim, output_dim=output_dim,
+                               output_edge_dim=edge_dim, hidden_dim_processor_edge=hidden_dim_processor_edge,
+                               hidden_layers_processor_node=hidden_layers_processor_node,
+                               hidden_dim_processor_node=hidden_dim_processor_node,
+                               hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                               hidden_dim_decoder=hidden_dim_decoder, hidden_layers_decoder=hidden_layers_decoder,
+                               use_checkpointing=use_checkpointing, precision=precision)  # fmt: skip
+        dims = dict(self.encoder._dims)
+        dims.update(n_out=self.decoder.num_latlons, n_dec_edges=self.decoder._dims["n_dec_edges"], out_dim=output_dim,
+                    residual_dim=output_dim, hidden_dec=hidden_dim_decoder, hidden_layers_dec=hidden_layers_decoder,
+                    num_blocks=num_blocks)  # fmt: skip
+        self._engine = _Engine(dims, precision)
+        self._engine.graph_uploaders += [self.encoder._upload_graphs, self.decoder._upload_graphs]
+
+    def _named(self):
+        return [(k, v) for k, v in self.state_dict(keep_vars=True).items()]
+
+    def forward(self, features: torch.Tensor, t: int = 0) -> torch.Tensor:
+        if features.device.type != "cuda":
+            _no_host_path("GraphWeatherForecaster.forward")
+        if features.shape[-1] < self.feature_dim or self.output_dim != self.feature_dim:
+            # the reference fails at `out + start_features` (decoder.py:93) when output_dim != feature_dim
+            raise RuntimeError(f"output_dim ({self.output_dim}) must equal feature_dim ({self.feature_dim}) for the residual add")
+        B = features.shape[0]
+        plan = self._engine.ensure(features.device, B, self._named())
+        f = features.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, self.decoder.num_latlons, self.output_dim), dtype=torch.float32, device=f.device)
+        plan.forward(f, out)
+        return out
+
+
+@dataclass
+class GraphWeatherAssimilatorConfig:
+    """analysis.py:11-49"""
+
+    output_lat_lons: list
+    resolution: int = 2
+    observation_dim: int = 2
+    analysis_dim: int = 78
+    node_dim: int = 256
+    edge_dim: int = 256
+    num_blocks: int = 9
+    hidden_dim_processor_node: int = 256
+    hidden_dim_processor_edge: int = 256
+    hidden_layers_processor_node: int = 2
+    hidden_layers_processor_edge: int = 2
+    hidden_dim_decoder: int = 128
+    hidden_layers_decoder: int = 2
+    norm_type: str = "LayerNorm"
+    use_checkpointing: bool = False
+
+    def build(self) -> "GraphWeatherAssimilator":
+        return GraphWeatherAssimilator(**self.__dict__)
+
+
+class GraphWeatherAssimilator(nn.Module, PyTorchModelHubMixin):
+    """GraphWeatherAssimilator(output_lat_lons=..)(features, obs_lat_lon_heights): analysis.py:52-150."""
+
+    def __init__(self, output_lat_lons: list, resolution: int = 2, observation_dim: int = 2, analysis_dim: int = 78,
+                 node_dim: int = 256, edge_dim: int = 256, num_blocks: int = 9, hidden_dim_processor_node: int = 256,
+                 hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
+                 hidden_dim_decoder: int = 128, hidden_layers_decoder: int = 2, norm_type: str = "LayerNorm",
+                 use_checkpointing: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        output_lat_lons = _latlon_list(output_lat_lons)
+        self.encoder = AssimilatorEncoder(resolution=resolution, input_dim=observation_dim, output_dim=node_dim,
+                                          output_edge_dim=edge_dim, hidden_dim_processor_edge=hidden_dim_processor_edge,
+                                          hidden_layers_processor_node=hidden_layers_processor_node,
+                                          hidden_dim_processor_node=hidden_dim_processor_node,
+                                          hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                                          use_checkpointing=use_checkpointing, precision=precision)  # fmt: skip
+        self.processor = Processor(input_dim=node_dim, edge_dim=edge_dim, num_blocks=num_blocks,
+                                   hidden_dim_processor_edge=hidden_dim_processor_edge,
+                                   hidden_layers_processor_node=hidden_layers_processor_node,
+                                   hidden_dim_processor_node=hidden_dim_processor_node,
+                                   hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                                   precision=precision)  # fmt: skip
+        self.decoder = AssimilatorDecoder(lat_lons=output_lat_lons, resolution=resolution, input_dim=node_dim, output_dim=analysis_dim,
+                                          output_edge_dim=edge_dim, hidden_dim_processor_edge=hidden_dim_processor_edge,
+                                          hidden_layers_processor_node=hidden_layers_processor_node,
+                                          hidden_dim_processor_node=hidden_dim_processor_node,
+                                          hidden_layers_processor_edge=hidden_layers_processor_edge, mlp_norm_type=norm_type,
+                                          hidden_dim_decoder=hidden_dim_decoder, hidden_layers_decoder=hidden_layers_decoder,
+                                          use_checkpointing=use_checkpointing, precision=precision)  # fmt: skip
+        dims = dict(self.encoder._dims)
+        dims.update(n_out=self.decoder.num_latlons, n_dec_edges=self.decoder._dims["n_dec_edges"], out_dim=analysis_dim,
+                    residual_dim=0, hidden_dec=hidden_dim_decoder, hidden_layers_dec=hidden_layers_decoder, num_blocks=num_blocks)  # fmt: skip
+        self.analysis_dim = analysis_dim
+        self._engine = _Engine(dims, precision)
+        self._engine.graph_uploaders += [self.encoder._upload_graphs, self.decoder._upload_graphs]
+
+    def forward(self, features: torch.Tensor, obs_lat_lon_heights: torch.Tensor) -> torch.Tensor:
+        if features.device.type != "cuda":
+            _no_host_path("GraphWeatherAssimilator.forward")
+        B, nobs = features.shape[0], obs_lat_lon_heights.shape[0]
+        named = [(k, v) for k, v in self.state_dict(keep_vars=True).items()]
+        plan = self._engine.ensure(features.device, B, named, grow=dict(n_in=nobs))
+        self.encoder._upload_obs(plan, obs_lat_lon_heights)
+        f = features.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, self.decoder.num_latlons, self.analysis_dim), dtype=torch.float32, device=f.device)
+        plan.forward(f, out)
+        return out

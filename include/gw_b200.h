@@ -1,0 +1,139 @@
+/* gw_b200.h -- C ABI of libgwb200.so: the B200 (sm_100a) encode-process-decode forward of graph_weather.
+ *
+ * The reference is pure Python (no native code, no FFI), so there is no existing C interface
+ * to mirror; each entry point below names the reference Python call it replaces.  A maintainer binds this library
+ * from Python with ctypes (INTEGRATION.md shows the stub); graph_weather_b200/_capi.py is that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers unless the name says host; all floating point is fp32,
+ *     row-major contiguous; indices are int32 (the reference's int64 edge_index is narrowed by the caller).
+ *   - every function returns 0 on success, non-zero on failure; gw_last_error() gives the message
+ *     (thread-local).  Nothing throws across the ABI.  There is NO CPU fallback: every compute entry point
+ *     fails if no CUDA device / kernel image is available.
+ *   - the caller owns every buffer it passes.  The plan owns only its scratch, packed weights and the
+ *     weight-constant tensors it precomputes.  One plan per device and stream; no global state; plans are
+ *     independent (one per GPU rank).
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef GW_B200_H
+#define GW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_ABI_VERSION 1
+
+/* arithmetic mode of the MLP contractions */
+#define GW_PREC_FP32_SIMT 0 /* fp32 FFMA on CUDA cores (exact fp32; any hidden size)                              */
+#define GW_PREC_FP32_TC 1   /* tcgen05 kind::f16, each fp32 operand split hi+lo (2x fp16), 3 MMAs, fp32 accumulate  */
+#define GW_PREC_BF16_TC 2   /* tcgen05 kind::f16 bf16 operands, single MMA, fp32 accumulate (configs 3/4)            */
+
+typedef struct gw_plan gw_plan; /* opaque */
+
+/* Sizes of one model + graph set.  Mirrors the constructor arguments of GraphWeatherForecaster (forecast.py:64-84)
+ * and GraphWeatherAssimilator (analysis.py:55-72) plus the graph sizes the reference derives from lat_lons. */
+typedef struct gw_dims {
+  int32_t n_in;        /* input lat/lon (or observation) points: encoder.num_latlons                 */
+  int32_t n_out;       /* output lat/lon points: decoder.num_latlons (== n_in for the forecaster)    */
+  int32_t n_mesh;      /* H3 cells: 2+120*7^res (5882 at res 2)                                      */
+  int32_t n_lat_edges; /* latent edges (41162 at res 2)                                              */
+  int32_t n_dec_edges; /* decoder edges (~7*n_out)                                                   */
+  int32_t in_dim;      /* feature_dim+aux_dim (102) / observation_dim (2)                            */
+  int32_t enc_edge_attr_dim; /* 2 (forecaster) or 3 (assimilator: + height)                          */
+  int32_t out_dim;     /* output_dim (78) / analysis_dim                                             */
+  int32_t residual_dim;/* >0: out += features[..., :residual_dim] (decoder.py:93); 0: none           */
+  int32_t node_dim, edge_dim;                 /* 256, 256 */
+  int32_t hidden_node, hidden_edge;           /* hidden_dim_processor_{node,edge}: 256 */
+  int32_t hidden_layers_node, hidden_layers_edge; /* 2, 2 */
+  int32_t hidden_dec, hidden_layers_dec;      /* 128, 2 */
+  int32_t num_blocks;                         /* processor blocks: 9 */
+  int32_t precision;                          /* GW_PREC_* */
+  int32_t max_batch;                          /* scratch is sized for this many samples per call */
+} gw_dims;
+
+/* One named fp32 parameter tensor; `name` is the reference state_dict key
+ * (e.g. "processor.graph_processor.blocks.3.edge_model.edge_mlp.model.0.weight", [256,768] row-major). */
+typedef struct gw_param {
+  const char* name;
+  const float* data; /* device */
+  int64_t rows, cols; /* 1-D tensors: rows = n, cols = 1 */
+} gw_param;
+
+int gw_abi_version(void);
+const char* gw_last_error(void);
+
+/* Replaces: GraphWeatherForecaster.__init__ / GraphWeatherAssimilator.__init__ module construction
+ * (forecast.py:129-170, analysis.py:96-134).  Allocates scratch for dims->max_batch samples on the current device. */
+int gw_plan_create(const gw_dims* dims, gw_plan** out_plan);
+int gw_plan_destroy(gw_plan* plan);
+/* bytes of device memory the plan holds (scratch + packed weights + constants) */
+int64_t gw_plan_device_bytes(const gw_plan* plan);
+
+/* Graph upload (all device int32 / fp32 arrays, copied into the plan).
+ * Replaces the graphs built at encoder.py:76-109,244-268 and assimilator_decoder.py:69-106.
+ *   encoder : one edge per input point p -> mesh slot enc_mesh[p] in [0,n_mesh); attr [n_in, enc_edge_attr_dim];
+ *             perm[n_in] = points sorted by mesh slot (ties in point order), ptr[n_mesh+1] = CSR over slots into perm.
+ *             n_in may be smaller than gw_dims.n_in (the assimilator rebuilds this graph per call,
+ *             assimilator_encoder.py:118,170-216); if weights are loaded its constants are refreshed.
+ *   latent  : edges SORTED BY TARGET: src[j], dst[j] (non-decreasing), ptr[n_mesh+1] CSR over dst; attr [El,2]
+ *   decoder : edges grouped by output point: src[j] mesh slot, ptr[n_out+1]; attr [Ed,2]                      */
+int gw_plan_set_encoder_graph(gw_plan* plan, int32_t n_in, const int32_t* enc_mesh, const int32_t* perm,
+                              const int32_t* ptr, const float* attr, void* stream);
+int gw_plan_set_latent_graph(gw_plan* plan, const int32_t* src, const int32_t* dst, const int32_t* ptr,
+                             const float* attr, void* stream);
+int gw_plan_set_decoder_graph(gw_plan* plan, const int32_t* src, const int32_t* ptr, const float* attr, void* stream);
+
+/* Replaces: load_state_dict on the reference module.  Looks parameters up by reference key name, packs them for
+ * the selected precision, then recomputes every weight-constant tensor (edge encoders on the fixed graphs,
+ * node_encoder(h3_nodes), the constant layer-1 terms).  Must follow the graph uploads; call again after any weight
+ * or graph change.  `params` is a host array of n entries whose `data` are device pointers.  The table may hold
+ * any subset of the groups "encoder.*", "processor.*", "decoder.*" (the reference's sub-modules can be built and
+ * called on their own, tests/test_model.py:20-119); a stage whose group or graph is missing fails when called. */
+int gw_plan_set_weights(gw_plan* plan, const gw_param* params, int32_t n, void* stream);
+
+/* Replaces: GraphWeatherForecaster.forward (forecast.py:215-247, constraint_type="none") and
+ * GraphWeatherAssimilator.forward (analysis.py:136-150) after its per-call input graph is uploaded.
+ *   features [batch, n_in, in_dim]  ->  out [batch, n_out, out_dim];  batch <= max_batch.                     */
+int gw_forward(gw_plan* plan, const float* features, float* out, int32_t batch, void* stream);
+
+/* Stage entry points (the reference's sub-module API, tests/test_model.py:106-119):
+ *   gw_encoder_forward   Encoder.forward   encoder.py:153-242        features -> x [batch*n_mesh, node_dim]
+ *   gw_processor_forward Processor.forward processor.py:83-128       x -> x   (in place allowed)
+ *   gw_decoder_forward   Decoder.forward   decoder.py:79-94 / AssimilatorDecoder.forward assimilator_decoder.py:131
+ *                        x [batch*n_mesh,node_dim] (+ start features [batch,n_out,start_ld], first residual_dim used)
+ * Mesh rows are in the encoder/decoder slot order (slot = H-1-rank), as in the reference.                       */
+int gw_encoder_forward(gw_plan* plan, const float* features, float* x_out, int32_t batch, void* stream);
+int gw_processor_forward(gw_plan* plan, const float* x_in, float* x_out, int32_t batch, void* stream);
+int gw_decoder_forward(gw_plan* plan, const float* x_in, const float* start_features, int32_t start_ld, float* out,
+                       int32_t batch, void* stream);
+/* Processor.forward on a CALLER-SUPPLIED graph (processor.py:83 takes edge_index / edge_attr as arguments):
+ * n_nodes x [n_nodes,node_dim], n_edges target-sorted edges (src, dst non-decreasing, ptr[n_nodes+1]) with initial
+ * edge features edge_attr [n_edges, edge_dim].  The reference's batch-replicated graph is simply a larger graph;
+ * capacity: n_nodes <= max_batch*n_mesh, n_edges <= max_batch*n_lat_edges. */
+int gw_processor_forward_graph(gw_plan* plan, const float* x_in, float* x_out, const float* edge_attr, int32_t n_nodes,
+                               int32_t n_edges, const int32_t* src, const int32_t* dst, const int32_t* ptr, void* stream);
+/* The encoded latent edge features Encoder.forward also returns (encoder.py:235-241), one sample's worth
+ * [n_lat_edges, edge_dim] in the plan's target-sorted edge order; copies into caller memory. */
+int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
+
+/* Per-launch device timing for bench.py's live roofline measurement.  When enabled, every kernel this library
+ * launches for the plan is bracketed by a cudaEvent pair recorded on the launching stream and attributed to a kernel
+ * class ("tag": enc_grid, enc_mesh, proc_p, proc_edge, proc_node, dec_p, dec_edge, dec_node, const).
+ * gw_timing_read synchronises `stream`, returns launches[] and summed milliseconds[] per tag (arrays of
+ * gw_timing_num_tags() entries) since the previous read, and resets the record. */
+int gw_timing_enable(gw_plan* plan, int32_t on);
+int32_t gw_timing_num_tags(void);
+const char* gw_timing_tag_name(int32_t tag);
+int gw_timing_read(gw_plan* plan, int64_t* launches, double* milliseconds, void* stream);
+
+/* Counters for bench.py: kernels launched by this library on the calling thread since the last reset. */
+int64_t gw_launch_count(void);
+void gw_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GW_B200_H */

@@ -1,0 +1,55 @@
+"""Quick device probe: time the forward at a named grid/batch and print per-kernel-class device time."""
+import argparse
+import json
+import sys
+import os
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--step", type=float, default=1.0)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--precision", default="fp32_simt")
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    ge.build()
+    from graph_weather_b200 import GraphWeatherForecaster
+
+    n_lat, n_lon = int(round(180 / a.step)), int(round(360 / a.step))
+    ll = [(-90.0 + a.step * i, a.step * j) for i in range(n_lat) for j in range(n_lon)]
+    t0 = time.time()
+    torch.manual_seed(42)
+    model = GraphWeatherForecaster(ll, precision=a.precision).cuda().eval()
+    print(f"construct {time.time() - t0:.1f}s  N={len(ll)} Ed={model.decoder._g_dec.src.size}", flush=True)
+    x = torch.randn(a.batch, len(ll), 102, device="cuda")
+    t0 = time.time()
+    y = model(x)
+    torch.cuda.synchronize()
+    print(f"first call {time.time() - t0:.2f}s  plan bytes {model._engine.plan.device_bytes() / 2**30:.2f} GiB  finite={bool(torch.isfinite(y).all())}", flush=True)
+    plan = model._engine.plan
+    for _ in range(2):
+        model(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        model(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    plan.timing_enable(True)
+    for _ in range(a.iters):
+        model(x)
+    tags = plan.timing_read()
+    plan.timing_enable(False)
+    print(json.dumps({"ms_per_step": ms, "steps_per_s": 1000 / ms, "tags": {k: (c // a.iters, round(v / a.iters, 3)) for k, (c, v) in tags.items() if c}}))
+
+
+if __name__ == "__main__":
+    main()
