@@ -52,6 +52,7 @@ _SIGNATURES = {
     "gw_processor_forward_graph": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gw_decoder_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "gw_latent_edge_features": (ctypes.c_int, [_vp, _vp, _vp]),
+    "gw_plan_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
     "gw_timing_enable": (ctypes.c_int, [_vp, _i32]),
     "gw_timing_num_tags": (_i32, []),
     "gw_timing_tag_name": (ctypes.c_char_p, [_i32]),
@@ -224,6 +225,16 @@ class Plan:
             ld = int(start.shape[-1]) if start is not None else 0
             _check(self.lib.gw_decoder_forward(self.handle, _ptr(x_in, torch.float32, d), sp, ld, _ptr(out, torch.float32, d),
                                                int(batch), _stream(d)))  # fmt: skip
+
+    def status(self) -> int:
+        """Synchronising read of the device status word (0 = ok); raises on a non-zero status."""
+        v = _i32(0)
+        with torch.cuda.device(self.device):
+            _check(self.lib.gw_plan_status(self.handle, ctypes.byref(v), _stream(self.device)))
+        if v.value:
+            raise RuntimeError(f"libgwb200 device status {v.value}: " + ("activation outside the fp16 range in precision 'fp32' (use 'fp32_simt'); " if v.value & 1 else "")
+                               + ("pipeline timeout; " if v.value & 2 else "") + ("shared memory misaligned" if v.value & 4 else ""))
+        return 0
 
     def timing_enable(self, on: bool):
         _check(self.lib.gw_timing_enable(self.handle, 1 if on else 0))

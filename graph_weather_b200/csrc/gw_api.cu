@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -119,6 +120,14 @@ struct gw_plan {
   DevBuf<float> ebuf0, ebuf1; // [max_batch*n_lat_edges, De]    latent edge state, double buffered
   DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
   size_t total_bytes = 0;
+  // tensor-core path: packed weight images (UMMA operand layout) and their descriptors
+  struct TcW { const void* p = nullptr; int K = 0, N = 0; float winv = 1.f; };
+  struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
+  DevBuf<unsigned char> tc_packed;
+  DevBuf<float> tc_absmax;
+  DevBuf<int32_t> tc_status;
+  TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node;
+  std::vector<TcMlp> tc_proc_edge, tc_proc_node;
   // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
   bool timing = false;
   int cur_tag = 0;
@@ -206,6 +215,33 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
   }
   return 0;
 }
+
+static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
+  ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
+  ch.status = p->tc_status.p;
+  cudaError_t e;
+  {
+    TimedLaunch t(p, st);
+    e = launch_chain_tc(ch, st);
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("tensor-core chain launch failed: ") + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+static bool is_tc(const gw_plan* p) { return p->d.precision != GW_PREC_FP32_SIMT; }
+
+static TcLayer tc_layer(const gw_plan::TcW& w, const float* bias, bool relu, bool feeds) {
+  TcLayer L;
+  L.Wp = w.p, L.K = w.K, L.N = w.N, L.wscale_inv = w.winv;
+  L.bias = bias, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
+  return L;
+}
+static void tc_ln(TcLayer& L, const Mlp& m, const RowSrc& residual) {
+  L.ln_g = m.ln_g, L.ln_b = m.ln_b, L.residual = residual;
+}
+static void tc_out(TcLayer& L, float* out, int ldo, int cols) { L.out = out, L.ldo = ldo, L.out_cols = cols; }
 
 // Runs an MLP whose first Linear is described by `first` (A sources / addends / weight slice already set; its
 // W/K/ldw/bias may have been overridden by the caller for factored layer 1) and whose remaining layers stream
@@ -329,6 +365,77 @@ static int bind_all(gw_plan* p) {
   return 0;
 }
 
+// Packs every weight panel the tensor-core chains stream.  Each panel is scaled by a power of two chosen from its
+// largest magnitude so that the fp16 lo parts of the split stay normal; the inverse scale is applied in the epilogue.
+static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
+  const gw_dims& d = p->d;
+  const int Dn = d.node_dim, De = d.edge_dim;
+  const int parts = (d.precision == GW_PREC_FP32_TC) ? 2 : 1;
+  struct Req { const float* W; int ldw, K, N; gw_plan::TcW* out; };
+  std::vector<Req> reqs;
+  auto want = [&](const float* W, int ldw, int K, int N, gw_plan::TcW* out) { reqs.push_back({W, ldw, K, N, out}); };
+  auto tail = [&](const Mlp& m, gw_plan::TcMlp& t) {
+    want(m.W[1], m.in[1], m.in[1], m.out[1], &t.w1);
+    want(m.W[2], m.in[2], m.in[2], m.out[2], &t.w2);
+  };
+  if (p->w_enc) {
+    want(p->enc_node.W[0], d.in_dim, d.in_dim, p->enc_node.out[0], &p->tc_enc_node.w0);
+    tail(p->enc_node, p->tc_enc_node);
+    want(p->enc_blk_edge.W[0], p->enc_blk_edge.in[0], Dn, p->enc_blk_edge.out[0], &p->tc_enc_edge.w0);  // src slice
+    tail(p->enc_blk_edge, p->tc_enc_edge);
+    want(p->enc_blk_node.W[0], p->enc_blk_node.in[0], Dn + De, p->enc_blk_node.out[0], &p->tc_enc_mnode.w0);
+    tail(p->enc_blk_node, p->tc_enc_mnode);
+  }
+  if (p->w_proc) {
+    p->tc_proc_edge.assign(d.num_blocks, gw_plan::TcMlp()), p->tc_proc_node.assign(d.num_blocks, gw_plan::TcMlp());
+    for (int k = 0; k < d.num_blocks; ++k) {
+      const Mlp& me = p->proc_edge[k];
+      want(me.W[0], me.in[0], Dn, me.out[0], &p->tc_proc_edge[k].w0);            // W1s
+      want(me.W[0] + Dn, me.in[0], Dn, me.out[0], &p->tc_proc_edge[k].w0b);      // W1d
+      want(me.W[0] + 2 * Dn, me.in[0], De, me.out[0], &p->tc_proc_edge[k].w0c);  // W1e
+      tail(me, p->tc_proc_edge[k]);
+      const Mlp& mn = p->proc_node[k];
+      want(mn.W[0], mn.in[0], Dn + De, mn.out[0], &p->tc_proc_node[k].w0);
+      tail(mn, p->tc_proc_node[k]);
+    }
+  }
+  if (p->w_dec) {
+    want(p->dec_blk_edge.W[0], p->dec_blk_edge.in[0], Dn, p->dec_blk_edge.out[0], &p->tc_dec_edge.w0);  // W1s
+    tail(p->dec_blk_edge, p->tc_dec_edge);
+    want(p->dec_blk_node.W[0] + Dn, p->dec_blk_node.in[0], De, p->dec_blk_node.out[0], &p->tc_dec_node.w0);  // agg half
+    tail(p->dec_blk_node, p->tc_dec_node);
+  }
+  const size_t n = reqs.size();
+  GW_TRY(p->tc_absmax.alloc(n));
+  GW_CUDA(cudaMemsetAsync(p->tc_absmax.p, 0, n * sizeof(float), st));
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    GW_CUDA(launch_absmax(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, p->tc_absmax.p + i, st));
+    total += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
+  }
+  std::vector<float> amax(n);
+  GW_CUDA(cudaMemcpyAsync(amax.data(), p->tc_absmax.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GW_CUDA(cudaStreamSynchronize(st));
+  if (p->tc_packed.n != total) GW_TRY(p->tc_packed.alloc(total));
+  size_t off = 0;
+  for (size_t i = 0; i < n; ++i) {
+    float scale = 1.f;
+    if (parts == 2 && amax[i] > 0.f && std::isfinite(amax[i])) {
+      int e = 0;
+      std::frexp(amax[i], &e);           // amax = f * 2^e, f in [0.5, 1)
+      scale = std::ldexp(1.f, 12 - e);   // amax * scale in [2048, 4096)
+    }
+    void* dst = p->tc_packed.p + off;
+    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, dst, st));
+    reqs[i].out->p = dst;
+    reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
+    reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
+    reqs[i].out->winv = 1.f / scale;
+    off += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // weight-constant precompute
 // ---------------------------------------------------------------------------------------------------------------
@@ -413,6 +520,48 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
     const float* f = features + (size_t)s0 * N * d.in_dim;
     float* xg = p->rows_n.p;
     float* eprime = p->rows_e.p;
+    if (is_tc(p)) {
+      // chain 1 (lat/lon rows): node_encoder (3 layers + LN) -> edge MLP of the encoder block (W1s . h + C1, 2 layers + LN)
+      // + e_enc residual -> e' rows.  Six GEMMs per row without leaving the SM.
+      p->cur_tag = TAG_ENC_GRID;
+      {
+        TcChain ch;
+        ch.rows_per_sample = N, ch.batch = cb;
+        ch.a0[0] = src_stream(f, d.in_dim, d.in_dim, N);
+        ch.K0 = p->tc_enc_node.w0.K;
+        const Mlp &mn = p->enc_node, &me = p->enc_blk_edge;
+        ch.layer[0] = tc_layer(p->tc_enc_node.w0, mn.b[0], true, true);
+        ch.layer[1] = tc_layer(p->tc_enc_node.w1, mn.b[1], true, true);
+        ch.layer[2] = tc_layer(p->tc_enc_node.w2, mn.b[2], false, true);
+        tc_ln(ch.layer[2], mn, none);
+        ch.layer[3] = tc_layer(p->tc_enc_edge.w0, nullptr, true, true);
+        ch.layer[3].add[0] = src_bcast(p->C1_enc.p, He, He);
+        ch.layer[4] = tc_layer(p->tc_enc_edge.w1, me.b[1], true, true);
+        ch.layer[5] = tc_layer(p->tc_enc_edge.w2, me.b[2], false, false);
+        tc_ln(ch.layer[5], me, src_bcast(p->e_enc.p, De, De));
+        tc_out(ch.layer[5], eprime, De, De);
+        ch.n_layers = 6;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      // chain 2 (mesh rows): [xm0 | sum of incoming e'] -> node MLP + LN + residual -> x
+      p->cur_tag = TAG_ENC_MESH;
+      {
+        TcChain ch;
+        ch.rows_per_sample = H, ch.batch = cb;
+        ch.a0[0] = src_bcast(p->xm0.p, Dn, Dn);
+        ch.a0[1] = src_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N);
+        ch.K0 = Dn + De;
+        const Mlp& m = p->enc_blk_node;
+        ch.layer[0] = tc_layer(p->tc_enc_mnode.w0, m.b[0], true, true);
+        ch.layer[1] = tc_layer(p->tc_enc_mnode.w1, m.b[1], true, true);
+        ch.layer[2] = tc_layer(p->tc_enc_mnode.w2, m.b[2], false, false);
+        tc_ln(ch.layer[2], m, src_bcast(p->xm0.p, Dn, Dn));
+        tc_out(ch.layer[2], x_out + (size_t)s0 * H * Dn, Dn, Dn);
+        ch.n_layers = 3;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      continue;
+    }
     // node_encoder on the lat/lon rows (encoder.py:205); the mesh rows are the constant xm0
     p->cur_tag = TAG_ENC_GRID;
     {
@@ -458,6 +607,61 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
   for (int k = 0; k < d.num_blocks; ++k) {
     const Mlp& me = p->proc_edge[k];
     const Mlp& mn = p->proc_node[k];
+    if (is_tc(p)) {
+      float* e_next = eb[k & 1];
+      float* x_next = (k == d.num_blocks - 1) ? x_out : xb[k & 1];
+      if (x_next == x_cur) x_next = xb[(k & 1) ^ 1];
+      const RowSrc e_src = e_cur ? src_stream(e_cur, De, De, El)
+                                 : (g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El));
+      p->cur_tag = TAG_PROC_P;
+      {  // P = x [W1s ; W1d]^T : one operand, two weight panels
+        TcChain ch;
+        ch.rows_per_sample = H, ch.batch = nb;
+        ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
+        ch.K0 = Dn;
+        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0, nullptr, false, false);
+        tc_out(ch.layer[0], p->P.p, 2 * He, He);
+        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w0b, nullptr, false, false);
+        ch.layer[1].reuse_a = 1;
+        tc_out(ch.layer[1], p->P.p + He, 2 * He, He);
+        ch.n_layers = 2;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      p->cur_tag = TAG_PROC_EDGE;
+      {  // e' = LN(W3 relu(W2 relu(W1e e + b1 + P_s[src] + P_d[dst]) + b2) + b3) + e
+        TcChain ch;
+        ch.rows_per_sample = El, ch.batch = nb;
+        ch.a0[0] = e_src;
+        ch.K0 = De;
+        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0c, me.b[0], true, true);
+        ch.layer[0].add[0] = src_gather(p->P.p, 2 * He, He, g.src, H, 0);
+        ch.layer[0].add[1] = src_gather(p->P.p, 2 * He, He, g.dst, H, He);
+        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w1, me.b[1], true, true);
+        ch.layer[2] = tc_layer(p->tc_proc_edge[k].w2, me.b[2], false, false);
+        tc_ln(ch.layer[2], me, e_src);
+        tc_out(ch.layer[2], e_next, De, De);
+        ch.n_layers = 3;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      p->cur_tag = TAG_PROC_NODE;
+      {  // x' = LN(MLP([x ; sum_in e'])) + x
+        TcChain ch;
+        ch.rows_per_sample = H, ch.batch = nb;
+        ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
+        ch.a0[1] = src_segsum(e_next, De, De, g.ptr, nullptr, El);
+        ch.K0 = Dn + De;
+        ch.layer[0] = tc_layer(p->tc_proc_node[k].w0, mn.b[0], true, true);
+        ch.layer[1] = tc_layer(p->tc_proc_node[k].w1, mn.b[1], true, true);
+        ch.layer[2] = tc_layer(p->tc_proc_node[k].w2, mn.b[2], false, false);
+        tc_ln(ch.layer[2], mn, src_stream(x_cur, Dn, Dn, H));
+        tc_out(ch.layer[2], x_next, Dn, Dn);
+        ch.n_layers = 3;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      x_cur = x_next;
+      e_cur = e_next;
+      continue;
+    }
     // P = x [W1s ; W1d]^T   (two column slices of the edge MLP's first Linear)
     p->cur_tag = TAG_PROC_P;
     for (int h = 0; h < 2; ++h) {
@@ -508,6 +712,55 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
     float* eprime = p->rows_e.p;
     float* xg = p->rows_n.p;
     const Mlp& me = p->dec_blk_edge;
+    if (is_tc(p)) {
+      const Mlp& mn = p->dec_blk_node;
+      p->cur_tag = TAG_DEC_P;
+      {
+        TcChain ch;
+        ch.rows_per_sample = H, ch.batch = cb;
+        ch.a0[0] = src_stream(x, Dn, Dn, H);
+        ch.K0 = Dn;
+        ch.layer[0] = tc_layer(p->tc_dec_edge.w0, nullptr, false, false);
+        tc_out(ch.layer[0], Pd, He, He);
+        ch.n_layers = 1;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      p->cur_tag = TAG_DEC_EDGE;
+      {  // layer 1 = relu(Pd[src] + E1) is the operand assembly; layers 2, 3 + LN + e_dec residual on the tensor cores
+        TcChain ch;
+        ch.rows_per_sample = Ed, ch.batch = cb;
+        ch.a0[0] = src_gather_bcast_relu(Pd, He, He, p->dec_src.p, H, p->E1_dec.p, He);
+        ch.K0 = He;
+        ch.layer[0] = tc_layer(p->tc_dec_edge.w1, me.b[1], true, true);
+        ch.layer[1] = tc_layer(p->tc_dec_edge.w2, me.b[2], false, false);
+        tc_ln(ch.layer[1], me, src_bcast(p->e_dec.p, De, De));
+        tc_out(ch.layer[1], eprime, De, De);
+        ch.n_layers = 2;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      p->cur_tag = TAG_DEC_NODE;
+      {  // lat/lon node update (x == 0, so only the aggregate half of W1 and no residual)
+        TcChain ch;
+        ch.rows_per_sample = No, ch.batch = cb;
+        ch.a0[0] = src_segsum(eprime, De, De, p->dec_ptr.p, nullptr, Ed);
+        ch.K0 = De;
+        ch.layer[0] = tc_layer(p->tc_dec_node.w0, mn.b[0], true, true);
+        ch.layer[1] = tc_layer(p->tc_dec_node.w1, mn.b[1], true, true);
+        ch.layer[2] = tc_layer(p->tc_dec_node.w2, mn.b[2], false, false);
+        tc_ln(ch.layer[2], mn, none);
+        tc_out(ch.layer[2], xg, Dn, Dn);
+        ch.n_layers = 3;
+        GW_TRY(run_chain(p, ch, st));
+      }
+      {  // node_decoder (256->128->128->out, no norm) + start-feature residual: CUDA-core row ops (small N)
+        const Mlp& m = p->dec_node_dec;
+        GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+        RowSrc res;
+        if (start && d.residual_dim > 0) res = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
+        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * d.out_dim, d.out_dim, st));
+      }
+      continue;
+    }
     p->cur_tag = TAG_DEC_P;
     {  // Pd = x W1s^T ; the dst operand (lat/lon nodes) is identically zero, assimilator_decoder.py:84,189-193
       GemmOp t;
@@ -576,7 +829,16 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   GW_CHECK(d.residual_dim == 0 || d.residual_dim == d.out_dim,
            "residual_dim must equal out_dim (the reference adds start features of the same width, decoder.py:93)");
   GW_CHECK(d.max_batch >= 1, "max_batch must be >= 1");
-  GW_CHECK(d.precision == GW_PREC_FP32_SIMT, "only GW_PREC_FP32_SIMT is built into this library version");
+  GW_CHECK(d.precision == GW_PREC_FP32_SIMT || d.precision == GW_PREC_FP32_TC || d.precision == GW_PREC_BF16_TC, "unknown precision");
+  if (d.precision != GW_PREC_FP32_SIMT) {
+    GW_CHECK(d.node_dim == 256 && d.edge_dim == 256 && d.hidden_node == 256 && d.hidden_edge == 256,
+             "the tensor-core chains are built for 256-wide node/edge/hidden dims (the reference default); use fp32_simt otherwise");
+    GW_CHECK(d.hidden_layers_node == 2 && d.hidden_layers_edge == 2, "the tensor-core chains are built for hidden_layers = 2");
+    int cc_major = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    GW_CHECK(cc_major == 10, "the tensor-core chains need an sm_100a device (tcgen05/TMEM)");
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) {
@@ -615,6 +877,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->xbuf0.alloc(B * d.n_mesh * Dn) | p->xbuf1.alloc(B * d.n_mesh * Dn);
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
+  rc |= p->tc_status.alloc(1);
   if (rc) {
     std::string keep = gw::g_err;
     gw_plan_destroy(p);
@@ -622,6 +885,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
     return 1;
   }
   GW_CUDA(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
+  GW_CUDA(cudaMemset(p->tc_status.p, 0, sizeof(int32_t)));
   p->n_in_cur = d.n_in;
   *out_plan = p;
   return 0;
@@ -635,6 +899,7 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
+  p->tc_packed.release(), p->tc_absmax.release(), p->tc_status.release();
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;
@@ -714,6 +979,7 @@ int gw_plan_set_weights(gw_plan* p, const gw_param* params, int32_t n, void* str
     off += (cnt + 63) / 64 * 64;
   }
   GW_TRY(gw::bind_all(p));
+  if (gw::is_tc(p)) GW_TRY(gw::pack_tc_weights(p, st));
   GW_TRY(gw::precompute_constants(p, st));
   return 0;
 }
@@ -763,6 +1029,16 @@ int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {
   GW_CHECK(p && edge_attr_out, "null argument");
   GW_CHECK(p->w_enc && p->have_lat, "needs the latent graph and encoder.* weights");
   GW_CUDA(cudaMemcpyAsync(edge_attr_out, p->e_lat.p, p->e_lat.bytes(), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int gw_plan_status(gw_plan* p, int32_t* status_out, void* stream) {
+  GW_CHECK(p && status_out, "null argument");
+  GW_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaMemcpyAsync(status_out, p->tc_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  GW_CUDA(cudaStreamSynchronize(st));
+  if (*status_out) GW_CUDA(cudaMemsetAsync(p->tc_status.p, 0, sizeof(int32_t), st));
   return 0;
 }
 

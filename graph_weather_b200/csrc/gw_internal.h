@@ -14,4 +14,13 @@ void set_error(const std::string& msg);
 // exact-fp32 CUDA-core execution of one row op (gw_simt.cu)
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream);
 
+// tcgen05 chain kernel (gw_tc.cu)
+cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream);
+// Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with
+// cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts).
+size_t tc_packed_bytes(int K_src, int N_src, int parts);
+cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, void* dst,
+                                cudaStream_t stream);
+cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream);
+
 }  // namespace gw

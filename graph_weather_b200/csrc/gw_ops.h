@@ -51,4 +51,35 @@ struct GemmOp {
   int32_t ldo = 0;
 };
 
+// ---- tensor-core chain (gw_tc.cu) --------------------------------------------------------------------------------
+// A chain runs up to TC_MAX_LAYERS row ops back to back on one 128-row tile without leaving the SM: the result of a
+// layer is split to fp16 hi/lo and written straight into the shared-memory A operand of the next layer.
+constexpr int TC_MAX_LAYERS = 8;
+
+struct TcLayer {
+  const void* Wp = nullptr;   // packed weights (see pack kernel in gw_tc.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major
+  int32_t K = 0, N = 0;       // K multiple of 64 (zero padded), N multiple of 16 (<= 256)
+  float wscale_inv = 1.f;     // weights are stored times a power of two; the accumulator is multiplied by this
+  const float* bias = nullptr;
+  RowSrc add[2];              // epilogue addends (SRC_BCAST / SRC_GATHER / SRC_STREAM), N wide
+  int32_t relu = 0;
+  const float* ln_g = nullptr;  // LayerNorm over N (eps 1e-5) if non-null
+  const float* ln_b = nullptr;
+  RowSrc residual;            // added after LN
+  float* out = nullptr;       // fp32 result rows -> out[(b*rows+i)*ldo + n], n < out_cols (null: not stored)
+  int32_t ldo = 0, out_cols = 0;
+  int32_t feeds_next = 0;     // result becomes the A operand of the next layer
+  int32_t reuse_a = 0;        // this layer multiplies the same A operand as the previous layer
+};
+
+struct TcChain {
+  int32_t rows_per_sample = 0, batch = 0;
+  RowSrc a0[2];               // stage-0 operand = concat(a0[0], a0[1]) zero-padded to K0
+  int32_t K0 = 0;             // multiple of 64
+  int32_t n_layers = 0;
+  int32_t split = 1;          // 1: fp16 hi+lo operands, 3 MMAs per product (fp32-faithful); 0: bf16 single MMA
+  int32_t* status = nullptr;  // device word: bit0 = operand exceeded the fp16 range, bit1 = pipeline timeout
+  TcLayer layer[TC_MAX_LAYERS];
+};
+
 }  // namespace gw

@@ -1,0 +1,600 @@
+// gw_tc.cu -- the fused MLP-chain kernel on Blackwell tensor cores (tcgen05 + TMEM), precision GW_PREC_FP32_TC / BF16_TC.
+//
+// One persistent CTA per SM walks 128-row tiles of a gw::TcChain.  For every tile the whole chain
+//     A0 = assemble(row sources)                                   (gather / CSR segment sum / relu(gather+const) ...)
+//     for each layer:  D = A . W^T  (tcgen05.mma, fp32 accumulate in TMEM)
+//                      v = D*s + bias + gathered addends ; ReLU | LayerNorm + residual
+//                      v -> global (fp32)  and/or  v -> split fp16 hi/lo -> shared memory = A operand of the next layer
+// runs without the activations ever leaving the SM.  This is the fusion BASELINE.json's north_star asks for: the
+// reference's x[row]/x[col] gathers, cat, 3 Linear + LayerNorm, residual and scatter_sum (graph_net_block.py:131-135,
+// 184-191) become one kernel per edge pass and one per node pass.
+//
+// fp32 fidelity on fp16 tensor cores: every fp32 operand a is split a = hi + lo (two fp16, 22 significand bits) and
+// each product is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (the dropped lo*lo term is 2^-22
+// relative).  Weights are pre-scaled by a power of two so that their lo parts stay in the fp16 normal range; the
+// scale is undone exactly in the epilogue.  Cost: 3 kind::f16 MMAs per product = 1.5x a TF32 MMA, half of 3xTF32.
+//
+// CTA layout (320 threads):
+//   warp 0   lane 0: weight producer  -- streams pre-swizzled weight panels global->smem with cp.async.bulk (UBLKCP)
+//   warp 1   lane 0: MMA issuer       -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256, K=16 per instruction
+//   warps 2-9      : 256 workers      -- thread (q,lane,h) owns tile row 32q+lane and the 32-column pieces 64s+32h;
+//                                        they assemble A0 and run every epilogue (tcgen05.ld from TMEM)
+// Shared memory (231,584 B): 4 A slots x [128 x 64] (hi|lo) = 128 KB, 3 weight stages x [256 x 64] = 96 KB, mbarriers.
+// TMEM: 512 columns = two 128x256 fp32 accumulators, so the MMAs of layer l+1 overlap the epilogue of layer l
+// piece by piece (the epilogue publishes each 64-column A slot as soon as it is written).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gw_internal.h"
+#include "gw_ops.h"
+
+namespace gw {
+
+constexpr int TILE_M = 128;
+constexpr int A_SLOTS = 4, B_STAGES = 3;
+constexpr int A_HALF_BYTES = TILE_M * 128;      // [128 rows x 64 halfs]
+constexpr int A_SLOT_BYTES = 2 * A_HALF_BYTES;  // hi | lo
+constexpr int B_STAGE_BYTES = 256 * 128;        // [256 rows x 64 halfs], hi OR lo panel
+constexpr int NUM_WORKERS = 256;
+constexpr int NUM_THREADS = 64 + NUM_WORKERS;
+constexpr int OFF_A = 0;
+constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
+constexpr int OFF_BAR = OFF_B + B_STAGES * B_STAGE_BYTES;  // 229376
+constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4;
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int OFF_LN = OFF_TMEM + 16;
+constexpr int SMEM_BYTES = OFF_LN + 2 * NUM_WORKERS * 4;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers (syntax checked against cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  After ~4 s the CTA flags status bit 1 and traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      if (status) atomicOr(status, 2);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// tcgen05.ld 32 lanes x 32 columns of 32-bit: thread t of the warp receives TMEM lane (lane_base+t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format [7,10)/[10,13) (0 = F16, 1 = BF16), K-major A and B,
+// N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int N, int bf16) {
+  uint32_t f = bf16 ? 1u : 0u;
+  return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// row-source pieces: 32 consecutive columns [c0, c0+32) of one logical row
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool vec4_ok(const float* base, int ld, int col) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0) && ((col & 3) == 0);
+}
+
+template <bool ACC>
+__device__ __forceinline__ void row_piece(const float* row, int col, int valid, bool vec, float (&v)[32]) {
+  // valid = number of columns of this piece that exist in the source (the rest read as 0)
+  if (vec && valid >= 32) {
+    const float4* p = reinterpret_cast<const float4*>(row + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t = __ldg(p + j);
+      if (ACC) {
+        v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
+      } else {
+        v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = (j < valid) ? __ldg(row + col + j) : 0.f;
+      if (ACC) v[j] += t; else v[j] = t;
+    }
+  }
+}
+
+// v (+)= columns [c, c+32) of source s for sample b, local row i; c is relative to the source (0 <= c < s.width)
+template <bool ACC>
+__device__ __forceinline__ void src_piece(const RowSrc& s, int b, int i, int c, float (&v)[32]) {
+  const int valid = min(32, s.width - c);
+  const int col = s.col0 + c;
+  const bool vec = vec4_ok(s.base, s.ld, col);
+  switch (s.kind) {
+    case SRC_STREAM:
+      row_piece<ACC>(s.base + ((size_t)b * s.src_rows + i) * s.ld, col, valid, vec, v);
+      break;
+    case SRC_BCAST:
+      row_piece<ACC>(s.base + (size_t)i * s.ld, col, valid, vec, v);
+      break;
+    case SRC_GATHER:
+      row_piece<ACC>(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld, col, valid, vec, v);
+      break;
+    case SRC_BGATHER:
+      row_piece<ACC>(s.base + (size_t)__ldg(s.idx + i) * s.ld, col, valid, vec, v);
+      break;
+    case SRC_SEGSUM: {
+      if (!ACC) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const int j0 = __ldg(s.ptr + i), j1 = __ldg(s.ptr + i + 1);
+      for (int j = j0; j < j1; ++j) {  // left-to-right, the order scatter_add visits the reference edge list
+        const int e = s.perm ? __ldg(s.perm + j) : j;
+        row_piece<true>(s.base + ((size_t)b * s.src_rows + e) * s.ld, col, valid, vec, v);
+      }
+      break;
+    }
+    case SRC_GATHER_BCAST_RELU: {
+      row_piece<false>(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld, col, valid, vec, v);
+      row_piece<true>(s.base2 + (size_t)i * s.ld2, c, valid, vec4_ok(s.base2, s.ld2, c), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    }
+    default:
+      if (!ACC) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+  }
+}
+
+// Split 32 fp32 values into fp16 hi/lo (or bf16) and store them as four 16-byte chunks per part into the swizzled
+// K-major operand tile: row r, logical 16B chunk j lives at chunk position j ^ (r & 7).
+__device__ __forceinline__ void store_operand_piece(uint8_t* slot, int r, int h, const float (&v)[32], bool split,
+                                                     float& amax) {
+  uint8_t* row_hi = slot + r * 128;
+  uint8_t* row_lo = row_hi + A_HALF_BYTES;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = v[8 * c + 2 * e], a1 = v[8 * c + 2 * e + 1];
+      amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+      if (split) {
+        const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+        const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+        __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+        hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+        lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+      } else {
+        __nv_bfloat162 bb = __floats2bfloat162_rn(a0, a1);
+        hi[e] = *reinterpret_cast<uint32_t*>(&bb);
+        lo[e] = 0;
+      }
+    }
+    const int chunk = ((h * 4 + c) ^ (r & 7)) * 16;
+    *reinterpret_cast<uint4*>(row_hi + chunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split) *reinterpret_cast<uint4*>(row_lo + chunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __grid_constant__ TcChain ch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = ch.rows_per_sample * ch.batch;
+  const int num_tiles = (R + TILE_M - 1) / TILE_M;
+  const bool split = ch.split != 0;
+  const int parts = split ? 2 : 1;
+
+  const uint32_t bar_full_a = sbase + OFF_BAR;                    // [A_SLOTS] workers -> MMA
+  const uint32_t bar_empty_a = bar_full_a + 8 * A_SLOTS;          // [A_SLOTS] MMA -> workers (tcgen05.commit)
+  const uint32_t bar_full_b = bar_empty_a + 8 * A_SLOTS;          // [B_STAGES] bulk copy -> MMA
+  const uint32_t bar_empty_b = bar_full_b + 8 * B_STAGES;         // [B_STAGES] MMA -> producer
+  const uint32_t bar_full_d = bar_empty_b + 8 * B_STAGES;         // [2] MMA -> workers: accumulator complete
+  const uint32_t bar_empty_d = bar_full_d + 16;                   // [2] workers -> MMA: accumulator drained
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+  float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
+  float* ln_y = ln_x + NUM_WORKERS;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) {  // SWIZZLE_128B operand tiles must be 1 KB aligned
+      if (ch.status) atomicOr(ch.status, 4);
+      __trap();
+    }
+    for (int i = 0; i < A_SLOTS; ++i) mbar_init(bar_full_a + 8 * i, NUM_WORKERS), mbar_init(bar_empty_a + 8 * i, 1);
+    for (int i = 0; i < B_STAGES; ++i) mbar_init(bar_full_b + 8 * i, 1), mbar_init(bar_empty_b + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_full_d + 8 * i, 1), mbar_init(bar_empty_d + 8 * i, NUM_WORKERS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== weight producer =====================================================
+    if (lane == 0) {
+      uint32_t bi = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < ch.n_layers; ++l) {
+          const TcLayer& L = ch.layer[l];
+          const uint32_t panel = (uint32_t)L.N * 128u;
+          const uint8_t* w = static_cast<const uint8_t*>(L.Wp);
+          const int nk = L.K >> 6;
+          for (int kc = 0; kc < nk; ++kc) {
+            for (int part = 0; part < parts; ++part, ++bi) {
+              const uint32_t stage = bi % B_STAGES, n = bi / B_STAGES;
+              mbar_wait(bar_empty_b + 8 * stage, (n & 1) ^ 1, ch.status);
+              mbar_expect_tx(bar_full_b + 8 * stage, panel);
+              bulk_g2s(sbase + OFF_B + stage * B_STAGE_BYTES, w + (size_t)(kc * parts + part) * panel, panel,
+                       bar_full_b + 8 * stage);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ==========================================================
+    if (lane == 0) {
+      uint32_t bi = 0, fi = 0, li = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t prev_first = fi;
+        for (int l = 0; l < ch.n_layers; ++l, ++li) {
+          const TcLayer& L = ch.layer[l];
+          const int nk = L.K >> 6;
+          const uint32_t idesc = umma_idesc(L.N, !split);
+          const uint32_t acc = li & 1, use = li >> 1;
+          mbar_wait(bar_empty_d + 8 * acc, (use & 1) ^ 1, ch.status);  // epilogue of layer li-2 has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          const uint32_t first = L.reuse_a ? prev_first : fi;
+          const bool last_use = !(l + 1 < ch.n_layers && ch.layer[l + 1].reuse_a);
+          for (int kc = 0; kc < nk; ++kc) {
+            const uint32_t f = first + kc, slot = f % A_SLOTS, n = f / A_SLOTS;
+            if (!L.reuse_a) mbar_wait(bar_full_a + 8 * slot, n & 1, ch.status);
+            const uint32_t a_hi = sbase + OFF_A + slot * A_SLOT_BYTES, a_lo = a_hi + A_HALF_BYTES;
+            {  // hi weight panel: A_hi.B_hi (+ A_lo.B_hi)
+              const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
+              mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
+              tc_fence_after();
+              const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, (kc | ks) != 0);
+              if (split) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_lo + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
+              }
+              tc_commit(bar_empty_b + 8 * stage);
+              ++bi;
+            }
+            if (split) {  // lo weight panel: A_hi.B_lo
+              const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
+              mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
+              tc_fence_after();
+              const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
+              tc_commit(bar_empty_b + 8 * stage);
+              ++bi;
+            }
+            if (last_use) tc_commit(bar_empty_a + 8 * slot);  // the operand slot may be refilled
+          }
+          tc_commit(bar_full_d + 8 * acc);  // accumulator complete -> epilogue
+          if (!L.reuse_a) {
+            prev_first = fi;
+            fi += nk;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== workers: operand assembly + epilogues ==============================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;       // which 32-column half of every 64-column slot this thread owns
+    const int r = 32 * q + lane;         // tile row
+    const int wtid = h * 128 + r;        // 0..255
+    uint32_t fi = 0, li = 0;
+    float amax = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int grow = tile * TILE_M + r;
+      const bool valid = grow < R;
+      const int crow = valid ? grow : R - 1;  // clamped: out-of-range rows compute on a real row and are not stored
+      const int b = crow / ch.rows_per_sample, i = crow - b * ch.rows_per_sample;
+
+      // ---- stage 0: assemble the first A operand, chunk by chunk -------------------------------------------------
+      {
+        const int nk0 = ch.K0 >> 6;
+        const int w0 = ch.a0[0].width;
+        for (int c = 0; c < nk0; ++c, ++fi) {
+          const uint32_t slot = fi % A_SLOTS, n = fi / A_SLOTS;
+          float v[32];
+          const int col = 64 * c + 32 * h;
+          // a0[0].width is a multiple of 32 whenever a second source follows (checked on the host)
+          if (col < w0) {
+            src_piece<false>(ch.a0[0], b, i, col, v);
+          } else if (ch.a0[1].kind != SRC_NONE && col - w0 < ch.a0[1].width) {
+            src_piece<false>(ch.a0[1], b, i, col - w0, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
+          store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
+          fence_proxy_async();
+          mbar_arrive(bar_full_a + 8 * slot);
+        }
+      }
+
+      // ---- layers -------------------------------------------------------------------------------------------------
+      for (int l = 0; l < ch.n_layers; ++l, ++li) {
+        const TcLayer& L = ch.layer[l];
+        const uint32_t acc = li & 1, use = li >> 1;
+        const int npieces = (L.N + 63) >> 6;
+        mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
+        float mean = 0.f, rstd = 1.f;
+        if (L.ln_g) {
+          // LayerNorm statistics over the N outputs of this row; the row is shared by two threads (h = 0, 1).
+          // Two passes over TMEM (mean, then centred second moment) like torch's CPU kernel; TMEM reads are cheap.
+          float s1 = 0.f;
+          for (int s = 0; s < npieces; ++s) {
+            const int c0 = 64 * s + 32 * h;
+            if (c0 >= L.N) break;
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f);
+              s1 += (c0 + j < L.N) ? x : 0.f;
+            }
+          }
+          ln_x[wtid] = s1;
+          named_bar_workers();
+          mean = (s1 + ln_x[wtid ^ 128]) / (float)L.N;
+          float s2 = 0.f;
+          for (int s = 0; s < npieces; ++s) {
+            const int c0 = 64 * s + 32 * h;
+            if (c0 >= L.N) break;
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f) - mean;
+              s2 += (c0 + j < L.N) ? x * x : 0.f;
+            }
+          }
+          ln_y[wtid] = s2;
+          named_bar_workers();
+          rstd = 1.0f / sqrtf((s2 + ln_y[wtid ^ 128]) / (float)L.N + 1e-5f);
+        }
+        for (int s = 0; s < npieces; ++s) {
+          const int c0 = 64 * s + 32 * h;
+          float v[32];
+          if (c0 < L.N) {
+            tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f);
+            if (L.add[0].kind != SRC_NONE) src_piece<true>(L.add[0], b, i, c0, v);
+            if (L.add[1].kind != SRC_NONE) src_piece<true>(L.add[1], b, i, c0, v);
+            if (L.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (L.ln_g) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = (c0 + j < L.N) ? (v[j] - mean) * rstd * __ldg(L.ln_g + c0 + j) + __ldg(L.ln_b + c0 + j) : 0.f;
+            }
+            if (L.residual.kind != SRC_NONE) src_piece<true>(L.residual, b, i, c0, v);
+            if (L.out && valid && c0 < L.out_cols) {
+              float* o = L.out + (size_t)grow * L.ldo + c0;
+              if (c0 + 32 <= L.out_cols && vec4_ok(L.out, L.ldo, c0)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < L.out_cols) o[j] = v[j];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (L.feeds_next) {  // publish this 64-column slot of the next operand as soon as both halves are written
+            const uint32_t f = fi + s, slot = f % A_SLOTS, n = f / A_SLOTS;
+            mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
+            store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
+            fence_proxy_async();
+            mbar_arrive(bar_full_a + 8 * slot);
+          }
+        }
+        if (L.feeds_next) fi += npieces;
+        tc_fence_before();
+        mbar_arrive(bar_empty_d + 8 * acc);  // this thread no longer reads the accumulator
+      }
+    }
+    if (split && ch.status && amax > 60000.f) atomicOr(ch.status, 1);  // operand left the fp16 range: results invalid
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight packing (one-off per weight set)
+// ------------------------------------------------------------------------------------------------------------------
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+size_t tc_packed_bytes(int K_src, int N_src, int parts) {
+  return (size_t)(round_up(K_src, 64) / 64) * parts * round_up(N_src, 16) * 128;
+}
+
+// dst image: for chunk kc, part p: panel of N rows x 128 B; element (n, k): 16B chunk ((k%64)/8) ^ (n&7), half k%8
+__global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int K_src, int N_src, int Kp, int Np,
+                                       float wscale, int parts, uint8_t* __restrict__ dst) {
+  const size_t total = (size_t)Np * Kp;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(e / Kp), k = (int)(e % Kp);
+    const float w = (n < N_src && k < K_src) ? W[(size_t)n * ldw + k] * wscale : 0.f;
+    const int kc = k >> 6, kk = k & 63;
+    const size_t panel = (size_t)Np * 128;
+    const size_t off = (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + ((kk & 7) << 1));
+    if (parts == 2) {
+      const __half hi = __float2half_rn(w);
+      const __half lo = __float2half_rn(w - __half2float(hi));
+      *reinterpret_cast<__half*>(dst + (size_t)(kc * 2 + 0) * panel + off) = hi;
+      *reinterpret_cast<__half*>(dst + (size_t)(kc * 2 + 1) * panel + off) = lo;
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)kc * panel + off) = __float2bfloat16_rn(w);
+    }
+  }
+}
+
+cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, void* dst,
+                                cudaStream_t stream) {
+  const int Kp = round_up(K_src, 64), Np = round_up(N_src, 16);
+  gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, static_cast<uint8_t*>(dst));
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void gw_absmax_kernel(const float* __restrict__ W, int ldw, int K_src, int N_src, float* out_max) {
+  float m = 0.f;
+  const size_t total = (size_t)N_src * K_src;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(W[(e / K_src) * (size_t)ldw + (e % K_src)]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(m));  // m >= 0: int order == float order
+}
+
+cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream) {
+  gw_absmax_kernel<<<64, 256, 0, stream>>>(W, ldw, K_src, N_src, out_max);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------------------------
+cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream) {
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (num_sms[dev] == 0) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gw_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    num_sms[dev] = n;
+  }
+  const long long R = (long long)ch.rows_per_sample * ch.batch;
+  if (R <= 0 || ch.n_layers <= 0) return cudaSuccess;
+  // structural requirements of the kernel
+  if (ch.n_layers > TC_MAX_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
+  if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 31)) return cudaErrorInvalidValue;
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const TcLayer& L = ch.layer[l];
+    if (!L.Wp || (L.K & 63) || (L.N & 31) || L.N > 256 || L.N <= 0) return cudaErrorInvalidValue;
+    if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
+    if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;
+    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next)) return cudaErrorInvalidValue;
+  }
+  const int tiles = (int)((R + TILE_M - 1) / TILE_M);
+  const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+  gw_chain_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gw

@@ -17,6 +17,7 @@ there is no eager-PyTorch or CPU execution path -- CPU tensors raise.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -161,6 +162,12 @@ class _Engine:
         self._wfp = None
 
 
+def _maybe_check(plan):
+    """GW_B200_CHECK=1: synchronise after every forward and raise on a non-zero device status word (tests, debugging)."""
+    if os.environ.get("GW_B200_CHECK", "0") == "1":
+        plan.status()
+
+
 def _prefixed(prefix, module):
     return [(f"{prefix}.{k}", v) for k, v in module.state_dict(keep_vars=True).items() if torch.is_tensor(v)]
 
@@ -239,6 +246,7 @@ class Encoder(nn.Module):
         f = features.detach().to(torch.float32).contiguous()
         x = torch.empty((B * self.num_h3, self.output_dim), dtype=torch.float32, device=f.device)
         plan.encoder_forward(f, x)
+        _maybe_check(plan)
         ei, ea = self._latent_outputs(plan, B, f.device)
         return x, ei, ea
 
@@ -299,6 +307,7 @@ class Processor(nn.Module):
         plan = self._engine.ensure(x.device, 1, _prefixed("processor", self), grow=dict(n_mesh=n_nodes, n_lat_edges=int(src.numel())))
         out = torch.empty_like(x)
         plan.processor_forward_graph(x, out, ea, src, dst, ptr)
+        _maybe_check(plan)
         return out
 
 
@@ -353,6 +362,7 @@ class AssimilatorDecoder(nn.Module):
         plan = self._own_engine().ensure(x.device, batch_size, _prefixed("decoder", self))
         out = torch.empty((batch_size, self.num_latlons, self.output_dim), dtype=torch.float32, device=x.device)
         plan.decoder_forward(x, start, out, batch_size)
+        _maybe_check(plan)
         return out
 
     def forward(self, processor_features: torch.Tensor, batch_size: int) -> torch.Tensor:
@@ -448,6 +458,7 @@ class AssimilatorEncoder(nn.Module):
         f = features.detach().to(torch.float32).contiguous()
         x = torch.empty((B * self.num_h3, self.output_dim), dtype=torch.float32, device=f.device)
         plan.encoder_forward(f, x)
+        _maybe_check(plan)
         ei, ea = self._latent_outputs(plan, B, f.device)
         return x, ei, ea
 
@@ -549,6 +560,7 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
         f = features.detach().to(torch.float32).contiguous()
         out = torch.empty((B, self.decoder.num_latlons, self.output_dim), dtype=torch.float32, device=f.device)
         plan.forward(f, out)
+        _maybe_check(plan)
         return out
 
 
@@ -622,4 +634,5 @@ class GraphWeatherAssimilator(nn.Module, PyTorchModelHubMixin):
         f = features.detach().to(torch.float32).contiguous()
         out = torch.empty((B, self.decoder.num_latlons, self.analysis_dim), dtype=torch.float32, device=f.device)
         plan.forward(f, out)
+        _maybe_check(plan)
         return out

@@ -119,6 +119,11 @@ int gw_processor_forward_graph(gw_plan* plan, const float* x_in, float* x_out, c
  * [n_lat_edges, edge_dim] in the plan's target-sorted edge order; copies into caller memory. */
 int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
 
+/* Synchronises `stream` and returns (then clears) the plan's device status word: 0 = ok;
+ * bit 0: an activation left the fp16 range in GW_PREC_FP32_TC (results invalid: rerun with GW_PREC_FP32_SIMT);
+ * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment.  Non-zero must be treated as failure. */
+int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
+
 /* Per-launch device timing for bench.py's live roofline measurement.  When enabled, every kernel this library
  * launches for the plan is bracketed by a cudaEvent pair recorded on the launching stream and attributed to a kernel
  * class ("tag": enc_grid, enc_mesh, proc_p, proc_edge, proc_node, dec_p, dec_edge, dec_node, const).

@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("GW_B200_CHECK", "1")  # tests always read the device status word after a forward
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -13,7 +13,7 @@ import __graft_entry__ as ge
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-PRECISIONS = ["fp32_simt"]
+PRECISIONS = ["fp32_simt", "fp32"]  # exact-fp32 CUDA cores; tcgen05 fp16x2-split (fp32-faithful)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -109,8 +109,15 @@ def test_irregular_points_against_oracle(precision):
     model = GraphWeatherForecaster(ll, precision=precision).cuda()
     model.load_state_dict(sd)
     out = model(x.cuda()).cpu()
-    ref = restate.forecaster_forward(sd, restate.build_forecaster_graphs(ll), x)
-    assert float((out - ref).abs().max()) < TOL
+    # Replication caveat: the reference offsets sample i of its replicated encoder graph by
+    # i*max(edge_index)+i (encoder.py:212-218), which is only the node count when the highest mesh id occurs in an
+    # edge.  For this point set it does not, so the reference's batched result is misaligned for samples >= 1; the
+    # per-sample (== efficient_batching, encoder.py:168-196) result is the well-defined one and is what we compare.
+    g = restate.build_forecaster_graphs(ll)
+    assert int(g["enc_edge_index"].max()) < len(ll) + 5882 - 1
+    for b in range(3):
+        ref = restate.forecaster_forward(sd, g, x[b : b + 1])
+        assert float((out[b : b + 1] - ref).abs().max()) < TOL
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
