@@ -1,0 +1,52 @@
+"""world_size-2 gloo test of the N>1 host logic: batch sharding, the loss-boundary all-gather, max-over-ranks timing."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from graph_weather_b200.dist import all_gather_batch, max_over_ranks, shard_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_range(total, rank, world)
+    full = torch.arange(total * 3 * 2, dtype=torch.float32).reshape(total, 3, 2)
+    got = all_gather_batch(full[a:b] * 1.0, total)
+    mx = max_over_ranks(10.0 + rank, "cpu")
+    q.put((rank, bool(torch.equal(got, full)), mx))
+    dist.destroy_process_group()
+
+
+def _run(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert all(ok for _, ok, _ in res), res
+    assert all(mx == 11.0 for _, _, mx in res), res
+
+
+def test_shard_range():
+    assert [shard_range(8, r, 2) for r in range(2)] == [(0, 4), (4, 8)]
+    assert [shard_range(7, r, 3) for r in range(3)] == [(0, 3), (3, 5), (5, 7)]
+    assert shard_range(1, 1, 2) == (1, 1)
+
+
+def test_all_gather_even():
+    _run(8)
+
+
+def test_all_gather_uneven():
+    _run(7)
