@@ -121,12 +121,14 @@ struct gw_plan {
   DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
   size_t total_bytes = 0;
   // tensor-core path: packed weight images (UMMA operand layout) and their descriptors
-  struct TcW { const void* p = nullptr; int K = 0, N = 0; float winv = 1.f; };
+  struct TcW { const void* p = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; };
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
   DevBuf<int32_t> tc_status;
-  TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node;
+  TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node, tc_dec_out;
+  bool tc_dec_out_ok = false;  // node_decoder fits the chain kernel (hidden_dec multiple of 64, 2 hidden layers)
+  DevBuf<float> agg_mesh;     // [chunk*n_mesh, De] encoder aggregation (segment sums)
   std::vector<TcMlp> tc_proc_edge, tc_proc_node;
   // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
   bool timing = false;
@@ -234,7 +236,7 @@ static bool is_tc(const gw_plan* p) { return p->d.precision != GW_PREC_FP32_SIMT
 
 static TcLayer tc_layer(const gw_plan::TcW& w, const float* bias, bool relu, bool feeds) {
   TcLayer L;
-  L.Wp = w.p, L.K = w.K, L.N = w.N, L.wscale_inv = w.winv;
+  L.Wp = w.p, L.K = w.K, L.N = w.N, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
   L.bias = bias, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
   return L;
 }
@@ -404,6 +406,12 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
     tail(p->dec_blk_edge, p->tc_dec_edge);
     want(p->dec_blk_node.W[0] + Dn, p->dec_blk_node.in[0], De, p->dec_blk_node.out[0], &p->tc_dec_node.w0);  // agg half
     tail(p->dec_blk_node, p->tc_dec_node);
+    const Mlp& md = p->dec_node_dec;
+    p->tc_dec_out_ok = md.L == 2 && (d.hidden_dec % 64 == 0) && d.hidden_dec <= 256 && d.out_dim <= 256;
+    if (p->tc_dec_out_ok) {
+      want(md.W[0], md.in[0], md.in[0], md.out[0], &p->tc_dec_out.w0);
+      tail(md, p->tc_dec_out);
+    }
   }
   const size_t n = reqs.size();
   GW_TRY(p->tc_absmax.alloc(n));
@@ -430,6 +438,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
     reqs[i].out->p = dst;
     reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
     reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
+    reqs[i].out->n_valid = reqs[i].N;
     reqs[i].out->winv = 1.f / scale;
     off += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
   }
@@ -548,8 +557,12 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
       {
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = cb;
+        {  // the lat/lon -> mesh segments are very skewed: reduce them with one CTA per (cell, sample) first
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->agg_mesh.p, De, st));
+        }
         ch.a0[0] = src_bcast(p->xm0.p, Dn, Dn);
-        ch.a0[1] = src_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N);
+        ch.a0[1] = src_stream(p->agg_mesh.p, De, De, H);
         ch.K0 = Dn + De;
         const Mlp& m = p->enc_blk_node;
         ch.layer[0] = tc_layer(p->tc_enc_mnode.w0, m.b[0], true, true);
@@ -614,17 +627,14 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
       const RowSrc e_src = e_cur ? src_stream(e_cur, De, De, El)
                                  : (g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El));
       p->cur_tag = TAG_PROC_P;
-      {  // P = x [W1s ; W1d]^T : one operand, two weight panels
+      for (int half = 0; half < 2; ++half) {  // P = x [W1s ; W1d]^T : one weight panel per launch
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
         ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
         ch.K0 = Dn;
-        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0, nullptr, false, false);
-        tc_out(ch.layer[0], p->P.p, 2 * He, He);
-        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w0b, nullptr, false, false);
-        ch.layer[1].reuse_a = 1;
-        tc_out(ch.layer[1], p->P.p + He, 2 * He, He);
-        ch.n_layers = 2;
+        ch.layer[0] = tc_layer(half ? p->tc_proc_edge[k].w0b : p->tc_proc_edge[k].w0, nullptr, false, false);
+        tc_out(ch.layer[0], p->P.p + half * He, 2 * He, He);
+        ch.n_layers = 1;
         GW_TRY(run_chain(p, ch, st));
       }
       p->cur_tag = TAG_PROC_EDGE;
@@ -748,11 +758,24 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
         ch.layer[1] = tc_layer(p->tc_dec_node.w1, mn.b[1], true, true);
         ch.layer[2] = tc_layer(p->tc_dec_node.w2, mn.b[2], false, false);
         tc_ln(ch.layer[2], mn, none);
+        if (p->tc_dec_out_ok) {  // node_decoder (256->128->128->out, no norm) + start-feature residual in the same chain
+          const Mlp& m = p->dec_node_dec;
+          ch.layer[2].feeds_next = 1;
+          ch.layer[3] = tc_layer(p->tc_dec_out.w0, m.b[0], true, true);
+          ch.layer[4] = tc_layer(p->tc_dec_out.w1, m.b[1], true, true);
+          ch.layer[5] = tc_layer(p->tc_dec_out.w2, m.b[2], false, false);
+          if (start && d.residual_dim > 0)
+            ch.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
+          tc_out(ch.layer[5], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
+          ch.n_layers = 6;
+          GW_TRY(run_chain(p, ch, st));
+          continue;
+        }
         tc_out(ch.layer[2], xg, Dn, Dn);
         ch.n_layers = 3;
         GW_TRY(run_chain(p, ch, st));
       }
-      {  // node_decoder (256->128->128->out, no norm) + start-feature residual: CUDA-core row ops (small N)
+      {  // node_decoder on the CUDA cores when its shape does not fit the chain kernel
         const Mlp& m = p->dec_node_dec;
         GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
         RowSrc res;
@@ -878,6 +901,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
   rc |= p->tc_status.alloc(1);
+  rc |= p->agg_mesh.alloc(chunk * d.n_mesh * De);
   if (rc) {
     std::string keep = gw::g_err;
     gw_plan_destroy(p);
@@ -899,7 +923,7 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
-  p->tc_packed.release(), p->tc_absmax.release(), p->tc_status.release();
+  p->tc_packed.release(), p->tc_absmax.release(), p->tc_status.release(), p->agg_mesh.release();
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;

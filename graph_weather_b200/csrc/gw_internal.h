@@ -14,6 +14,9 @@ void set_error(const std::string& msg);
 // exact-fp32 CUDA-core execution of one row op (gw_simt.cu)
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream);
 
+cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows,
+                          int rows, int batch, float* out, int ldo, cudaStream_t stream);
+
 // tcgen05 chain kernel (gw_tc.cu)
 cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream);
 // Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with

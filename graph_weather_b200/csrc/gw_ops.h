@@ -59,6 +59,7 @@ constexpr int TC_MAX_LAYERS = 8;
 struct TcLayer {
   const void* Wp = nullptr;   // packed weights (see pack kernel in gw_tc.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major
   int32_t K = 0, N = 0;       // K multiple of 64 (zero padded), N multiple of 16 (<= 256)
+  int32_t n_valid = 0;        // real output columns (<= N); bias / LN parameters / addends exist only for these
   float wscale_inv = 1.f;     // weights are stored times a power of two; the accumulator is multiplied by this
   const float* bias = nullptr;
   RowSrc add[2];              // epilogue addends (SRC_BCAST / SRC_GATHER / SRC_STREAM), N wide

@@ -166,6 +166,34 @@ __global__ void __launch_bounds__(NT) gw_rowop_f32_kernel(const GemmOp op) {
   }
 }
 
+// out[(b*rows + i), :] = sum over CSR segment i of base rows (left to right, the reference's scatter_add order).
+// One 64-thread CTA per (segment, sample): float4 per thread across 256 columns, rows read fully coalesced.  Serves the
+// encoder's lat/lon -> mesh aggregation, whose segments are very skewed (a polar cell collects thousands of points).
+__global__ void __launch_bounds__(64) gw_segsum_kernel(const float* __restrict__ base, int ld, int width,
+                                                       const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                                                       int src_rows, int rows, float* __restrict__ out, int ldo) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int j0 = __ldg(ptr + i), j1 = __ldg(ptr + i + 1);
+  for (int c = threadIdx.x * 4; c < width; c += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = j0; j < j1; ++j) {
+      const int e = perm ? __ldg(perm + j) : j;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(base + ((size_t)b * src_rows + e) * ld + c));
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)b * rows + i) * ldo + c) = acc;
+  }
+}
+
+cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows,
+                          int rows, int batch, float* out, int ldo, cudaStream_t stream) {
+  if (rows <= 0 || batch <= 0) return cudaSuccess;
+  if ((width & 3) || (ld & 3) || (ldo & 3)) return cudaErrorInvalidValue;
+  gw_segsum_kernel<<<dim3(rows, batch), 64, 0, stream>>>(base, ld, width, ptr, perm, src_rows, rows, out, ldo);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream) {
   const long long R = (long long)op.rows_per_sample * op.batch;
   if (R <= 0 || op.N <= 0) return cudaSuccess;

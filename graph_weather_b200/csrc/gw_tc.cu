@@ -14,14 +14,20 @@
 // relative).  Weights are pre-scaled by a power of two so that their lo parts stay in the fp16 normal range; the
 // scale is undone exactly in the epilogue.  Cost: 3 kind::f16 MMAs per product = 1.5x a TF32 MMA, half of 3xTF32.
 //
-// CTA layout (320 threads):
-//   warp 0   lane 0: weight producer  -- streams pre-swizzled weight panels global->smem with cp.async.bulk (UBLKCP)
-//   warp 1   lane 0: MMA issuer       -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256, K=16 per instruction
-//   warps 2-9      : 256 workers      -- thread (q,lane,h) owns tile row 32q+lane and the 32-column pieces 64s+32h;
-//                                        they assemble A0 and run every epilogue (tcgen05.ld from TMEM)
-// Shared memory (231,584 B): 4 A slots x [128 x 64] (hi|lo) = 128 KB, 3 weight stages x [256 x 64] = 96 KB, mbarriers.
-// TMEM: 512 columns = two 128x256 fp32 accumulators, so the MMAs of layer l+1 overlap the epilogue of layer l
-// piece by piece (the epilogue publishes each 64-column A slot as soon as it is written).
+// CTA layout (448 threads, one persistent CTA per SM):
+//   warp 0   lane 0: weight producer -- streams pre-swizzled weight panels global->smem with cp.async.bulk (UBLKCP)
+//   warp 1   lane 0: MMA issuer      -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256, K=16 per instruction
+//   warps 2-5      : 128 movers      -- ALL global row traffic: gather / stream / CSR segment-sum rows into padded
+//                                       fp32 staging pieces (cp.async 16 B or vector loads, 8 lanes per 128 B row line)
+//                                       and coalesced stores of finished rows out of staging
+//   warps 6-13     : 256 workers     -- thread (q,lane,h) owns tile row 32q+lane and the 32-column pieces 64s+32h; they
+//                                       convert staged rows to fp16 hi/lo operands and run every epilogue from TMEM;
+//                                       they touch TMEM and shared memory only
+// Shared memory: 2 A slots x [128 x 64] (hi|lo) = 64 KB, 3 weight stages x [256 x 64] = 96 KB, 3 staging pieces
+// [128 x 32] fp32 = 54 KB, mbarriers.  TMEM: 512 columns = two 128x256 fp32 accumulators, so the MMAs of layer l+1
+// overlap the epilogue of layer l chunk by chunk, and the movers prefetch the next tile during the last epilogue.
+// Tiles are batch-major (same rows of consecutive samples are neighbours) so broadcast constants are read from HBM
+// once and served to the other samples from L2.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -33,21 +39,26 @@
 namespace gw {
 
 constexpr int TILE_M = 128;
-constexpr int A_SLOTS = 4, B_STAGES = 3;
+constexpr int A_SLOTS = 2, B_STAGES = 3, ST_BUFS = 3;
 constexpr int A_HALF_BYTES = TILE_M * 128;      // [128 rows x 64 halfs]
 constexpr int A_SLOT_BYTES = 2 * A_HALF_BYTES;  // hi | lo
 constexpr int B_STAGE_BYTES = 256 * 128;        // [256 rows x 64 halfs], hi OR lo panel
+constexpr int ST_STRIDE = 144;                  // staging row: 32 fp32 + 16 B pad (conflict-free 16-byte row access)
+constexpr int ST_BYTES = TILE_M * ST_STRIDE;    // one [128 rows x 32 cols] fp32 piece
+constexpr int NUM_MOVERS = 128;
 constexpr int NUM_WORKERS = 256;
-constexpr int NUM_THREADS = 64 + NUM_WORKERS;
+constexpr int NUM_THREADS = 64 + NUM_MOVERS + NUM_WORKERS;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
-constexpr int OFF_BAR = OFF_B + B_STAGES * B_STAGE_BYTES;  // 229376
-constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4;
+constexpr int OFF_ST = OFF_B + B_STAGES * B_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_ST + ST_BUFS * ST_BYTES;
+constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4 + 2 * ST_BUFS;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_LN = OFF_TMEM + 16;
 constexpr int SMEM_BYTES = OFF_LN + 2 * NUM_WORKERS * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
+static_assert(OFF_ST % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
 // ------------------------------------------------------------------------------------------------------------------
 // PTX wrappers (syntax checked against cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp)
@@ -144,78 +155,76 @@ __device__ __forceinline__ uint32_t umma_idesc(int N, int bf16) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// row-source pieces: 32 consecutive columns [c0, c0+32) of one logical row
+// movers: global rows <-> padded fp32 staging pieces
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ bool vec4_ok(const float* base, int ld, int col) {
   return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0) && ((col & 3) == 0);
 }
-
-template <bool ACC>
-__device__ __forceinline__ void row_piece(const float* row, int col, int valid, bool vec, float (&v)[32]) {
-  // valid = number of columns of this piece that exist in the source (the rest read as 0)
-  if (vec && valid >= 32) {
-    const float4* p = reinterpret_cast<const float4*>(row + col);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 t = __ldg(p + j);
-      if (ACC) {
-        v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
-      } else {
-        v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float t = (j < valid) ? __ldg(row + col + j) : 0.f;
-      if (ACC) v[j] += t; else v[j] = t;
-    }
+__device__ __forceinline__ bool is_simple(int kind) {
+  return kind == SRC_STREAM || kind == SRC_BCAST || kind == SRC_GATHER || kind == SRC_BGATHER;
+}
+// row pointer of a simple source for sample b, local row i
+__device__ __forceinline__ const float* simple_row(const RowSrc& s, int b, int i) {
+  switch (s.kind) {
+    case SRC_STREAM: return s.base + ((size_t)b * s.src_rows + i) * s.ld + s.col0;
+    case SRC_BCAST: return s.base + (size_t)i * s.ld + s.col0;
+    case SRC_GATHER: return s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld + s.col0;
+    default: return s.base + (size_t)__ldg(s.idx + i) * s.ld + s.col0;  // SRC_BGATHER
   }
 }
+// 4 consecutive columns [c, c+4) of a row pointer; columns >= width read as 0
+__device__ __forceinline__ float4 load4(const float* row, int c, int width, bool vec) {
+  if (vec && c + 4 <= width) return __ldg(reinterpret_cast<const float4*>(row + c));
+  float4 v;
+  v.x = (c + 0 < width) ? __ldg(row + c + 0) : 0.f;
+  v.y = (c + 1 < width) ? __ldg(row + c + 1) : 0.f;
+  v.z = (c + 2 < width) ? __ldg(row + c + 2) : 0.f;
+  v.w = (c + 3 < width) ? __ldg(row + c + 3) : 0.f;
+  return v;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// v (+)= columns [c, c+32) of source s for sample b, local row i; c is relative to the source (0 <= c < s.width)
-template <bool ACC>
-__device__ __forceinline__ void src_piece(const RowSrc& s, int b, int i, int c, float (&v)[32]) {
-  const int valid = min(32, s.width - c);
-  const int col = s.col0 + c;
-  const bool vec = vec4_ok(s.base, s.ld, col);
+// value of source s at (sample b, local row i, columns [c, c+4)) -- any source kind
+__device__ __forceinline__ float4 src_load4(const RowSrc& s, int b, int i, int c) {
+  if (c >= s.width) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = vec4_ok(s.base, s.ld, s.col0 + c);
   switch (s.kind) {
     case SRC_STREAM:
-      row_piece<ACC>(s.base + ((size_t)b * s.src_rows + i) * s.ld, col, valid, vec, v);
-      break;
     case SRC_BCAST:
-      row_piece<ACC>(s.base + (size_t)i * s.ld, col, valid, vec, v);
-      break;
     case SRC_GATHER:
-      row_piece<ACC>(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld, col, valid, vec, v);
-      break;
     case SRC_BGATHER:
-      row_piece<ACC>(s.base + (size_t)__ldg(s.idx + i) * s.ld, col, valid, vec, v);
-      break;
+      return load4(simple_row(s, b, i), c, s.width, vec);
     case SRC_SEGSUM: {
-      if (!ACC) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       const int j0 = __ldg(s.ptr + i), j1 = __ldg(s.ptr + i + 1);
-      for (int j = j0; j < j1; ++j) {  // left-to-right, the order scatter_add visits the reference edge list
+      for (int j = j0; j < j1; ++j) {  // left to right: the order scatter_add visits the reference edge list
         const int e = s.perm ? __ldg(s.perm + j) : j;
-        row_piece<true>(s.base + ((size_t)b * s.src_rows + e) * s.ld, col, valid, vec, v);
+        acc = add4(acc, load4(s.base + ((size_t)b * s.src_rows + e) * s.ld + s.col0, c, s.width, vec));
       }
-      break;
+      return acc;
     }
     case SRC_GATHER_BCAST_RELU: {
-      row_piece<false>(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld, col, valid, vec, v);
-      row_piece<true>(s.base2 + (size_t)i * s.ld2, c, valid, vec4_ok(s.base2, s.ld2, c), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      break;
+      float4 v = load4(s.base + ((size_t)b * s.src_rows + __ldg(s.idx + i)) * s.ld + s.col0, c, s.width, vec);
+      v = add4(v, load4(s.base2 + (size_t)i * s.ld2, c, s.width, vec4_ok(s.base2, s.ld2, c)));
+      return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
     }
     default:
-      if (!ACC) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
+      return make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -250,6 +259,11 @@ __device__ __forceinline__ void store_operand_piece(uint8_t* slot, int r, int h,
   }
 }
 
+struct Retire {  // what a mover needs to know to finish a staged piece: store it out (if it has an output)
+  float* out;    // first output row of the tile (null: nothing to store)
+  int ldo, out_cols, c0, nvalid;
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -257,17 +271,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = ch.rows_per_sample * ch.batch;
-  const int num_tiles = (R + TILE_M - 1) / TILE_M;
+  const int rows = ch.rows_per_sample, batch = ch.batch;
+  const int tiles_per_sample = (rows + TILE_M - 1) / TILE_M;
+  const int num_tiles = tiles_per_sample * batch;  // batch-major: tile -> (sample = tile % batch, row block = tile / batch)
   const bool split = ch.split != 0;
   const int parts = split ? 2 : 1;
 
-  const uint32_t bar_full_a = sbase + OFF_BAR;                    // [A_SLOTS] workers -> MMA
-  const uint32_t bar_empty_a = bar_full_a + 8 * A_SLOTS;          // [A_SLOTS] MMA -> workers (tcgen05.commit)
-  const uint32_t bar_full_b = bar_empty_a + 8 * A_SLOTS;          // [B_STAGES] bulk copy -> MMA
-  const uint32_t bar_empty_b = bar_full_b + 8 * B_STAGES;         // [B_STAGES] MMA -> producer
-  const uint32_t bar_full_d = bar_empty_b + 8 * B_STAGES;         // [2] MMA -> workers: accumulator complete
-  const uint32_t bar_empty_d = bar_full_d + 16;                   // [2] workers -> MMA: accumulator drained
+  const uint32_t bar_full_a = sbase + OFF_BAR;              // [A_SLOTS] workers -> MMA
+  const uint32_t bar_empty_a = bar_full_a + 8 * A_SLOTS;    // [A_SLOTS] MMA -> workers (tcgen05.commit)
+  const uint32_t bar_full_b = bar_empty_a + 8 * A_SLOTS;    // [B_STAGES] bulk copy -> MMA
+  const uint32_t bar_empty_b = bar_full_b + 8 * B_STAGES;   // [B_STAGES] MMA -> producer
+  const uint32_t bar_full_d = bar_empty_b + 8 * B_STAGES;   // [2] MMA -> workers: accumulator complete
+  const uint32_t bar_empty_d = bar_full_d + 16;             // [2] workers -> MMA: accumulator drained
+  const uint32_t bar_st_ready = bar_empty_d + 16;           // [ST_BUFS] movers -> workers: staging piece filled / free
+  const uint32_t bar_st_done = bar_st_ready + 8 * ST_BUFS;  // [ST_BUFS] workers (one h group) -> movers: piece consumed / produced
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
   float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
   float* ln_y = ln_x + NUM_WORKERS;
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
     for (int i = 0; i < A_SLOTS; ++i) mbar_init(bar_full_a + 8 * i, NUM_WORKERS), mbar_init(bar_empty_a + 8 * i, 1);
     for (int i = 0; i < B_STAGES; ++i) mbar_init(bar_full_b + 8 * i, 1), mbar_init(bar_empty_b + 8 * i, 1);
     for (int i = 0; i < 2; ++i) mbar_init(bar_full_d + 8 * i, 1), mbar_init(bar_empty_d + 8 * i, NUM_WORKERS);
+    for (int i = 0; i < ST_BUFS; ++i) mbar_init(bar_st_ready + 8 * i, NUM_MOVERS), mbar_init(bar_st_done + 8 * i, NUM_WORKERS / 2);
     fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
           const bool last_use = !(l + 1 < ch.n_layers && ch.layer[l + 1].reuse_a);
           for (int kc = 0; kc < nk; ++kc) {
             const uint32_t f = first + kc, slot = f % A_SLOTS, n = f / A_SLOTS;
-            if (!L.reuse_a) mbar_wait(bar_full_a + 8 * slot, n & 1, ch.status);
+            mbar_wait(bar_full_a + 8 * slot, n & 1, ch.status);  // (already complete when the operand is re-used)
             const uint32_t a_hi = sbase + OFF_A + slot * A_SLOT_BYTES, a_lo = a_hi + A_HALF_BYTES;
             {  // hi weight panel: A_hi.B_hi (+ A_lo.B_hi)
               const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
@@ -369,96 +387,240 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
     }
+  } else if (warp < 6) {
+    // ===================================== movers ==============================================================
+    // Thread (rsub, ck) moves the 16-byte group ck of rows rsub, rsub+16, ..: 8 lanes cover one 128-byte row line.
+    const int mt = threadIdx.x - 64;
+    const int rsub = mt >> 3, ck = mt & 7;
+    uint32_t pn = 0;
+    Retire ring[ST_BUFS];
+#pragma unroll
+    for (int i = 0; i < ST_BUFS; ++i) ring[i].out = nullptr;
+
+    auto retire = [&](uint32_t p) {  // piece p: wait until its workers are done with it, then store its output rows
+      const uint32_t buf = p % ST_BUFS, use = p / ST_BUFS;
+      mbar_wait(bar_st_done + 8 * buf, use & 1, ch.status);
+      const Retire rt = ring[buf];
+      if (rt.out) {
+        const uint32_t st = sbase + OFF_ST + buf * ST_BYTES + ck * 16;
+        const int col = rt.c0 + 4 * ck;
+        const bool vec = vec4_ok(rt.out, rt.ldo, col) && col + 4 <= rt.out_cols;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rsub + 16 * j;
+          if (r < rt.nvalid && col < rt.out_cols) {
+            const float4 v = lds128(st + r * ST_STRIDE);
+            float* o = rt.out + (size_t)r * rt.ldo + col;
+            if (vec) {
+              *reinterpret_cast<float4*>(o) = v;
+            } else {
+              o[0] = v.x;
+              if (col + 1 < rt.out_cols) o[1] = v.y;
+              if (col + 2 < rt.out_cols) o[2] = v.z;
+              if (col + 3 < rt.out_cols) o[3] = v.w;
+            }
+          }
+        }
+      }
+    };
+    // piece: fill staging from up to two sources (summed); s0 may be SRC_NONE (output-only piece: just hand the buffer over)
+    auto piece = [&](const RowSrc& s0, const RowSrc& s1, int c, int bs, int i0, int nvalid, const Retire& rt) {
+      const uint32_t buf = pn % ST_BUFS;
+      if (pn >= ST_BUFS) retire(pn - ST_BUFS);
+      ring[buf] = rt;
+      const uint32_t st = sbase + OFF_ST + buf * ST_BYTES + ck * 16;
+      const uint32_t bar = bar_st_ready + 8 * buf;
+      const int col = c + 4 * ck;
+      if (s0.kind == SRC_NONE) {
+        mbar_arrive(bar);
+      } else if (s1.kind == SRC_NONE && is_simple(s0.kind) && vec4_ok(s0.base, s0.ld, s0.col0 + c) && c + 32 <= s0.width) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rsub + 16 * j;
+          const int i = i0 + min(r, nvalid - 1);  // rows past the end of the sample re-read the last valid row
+          cp_async16(st + r * ST_STRIDE, simple_row(s0, bs, i) + col);
+        }
+        cp_async_arrive_noinc(bar);
+      } else {
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+          const int r = rsub + 16 * j;
+          const int i = i0 + min(r, nvalid - 1);
+          float4 v = src_load4(s0, bs, i, col);
+          if (s1.kind != SRC_NONE) v = add4(v, src_load4(s1, bs, i, col));
+          sts128(st + r * ST_STRIDE, v);
+        }
+        mbar_arrive(bar);
+      }
+      ++pn;
+    };
+
+    const RowSrc none;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      Retire no_out;
+      no_out.out = nullptr, no_out.ldo = 0, no_out.out_cols = 0, no_out.c0 = 0, no_out.nvalid = nvalid;
+      // stage-0 operand pieces
+      const int nk0 = ch.K0 >> 6, w0 = ch.a0[0].width;
+      for (int c = 0; c < nk0; ++c) {
+        for (int h = 0; h < 2; ++h) {
+          const int col = 64 * c + 32 * h;
+          if (col < w0) {
+            piece(ch.a0[0], none, col, bs, i0, nvalid, no_out);
+          } else if (ch.a0[1].kind != SRC_NONE && col - w0 < ch.a0[1].width) {
+            piece(ch.a0[1], none, col - w0, bs, i0, nvalid, no_out);
+          } else {  // zero padding of K0: a source of width 0 reads as zeros
+            RowSrc z = ch.a0[0];
+            z.width = 0, z.kind = SRC_STREAM;
+            piece(z, z, col, bs, i0, nvalid, no_out);
+          }
+        }
+      }
+      for (int l = 0; l < ch.n_layers; ++l) {
+        const TcLayer& L = ch.layer[l];
+        const bool has_add = L.add[0].kind != SRC_NONE;
+        const bool has_ro = L.residual.kind != SRC_NONE || L.out != nullptr;
+        if (!has_add && !has_ro) continue;
+        const int np = (L.N + 63) >> 6;
+        for (int s = 0; s < np; ++s) {
+          if (has_add)
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = 64 * s + 32 * h;
+              if (c0 < L.N) piece(L.add[0], L.add[1], c0, bs, i0, nvalid, no_out);
+            }
+          if (has_ro)
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = 64 * s + 32 * h;
+              if (c0 < L.N) {
+                Retire rt = no_out;
+                if (L.out) {
+                  rt.out = L.out + ((size_t)bs * rows + i0) * L.ldo;
+                  rt.ldo = L.ldo, rt.out_cols = L.out_cols, rt.c0 = c0;
+                }
+                piece(L.residual, none, c0, bs, i0, nvalid, rt);
+              }
+            }
+        }
+      }
+    }
+    for (uint32_t p = (pn > ST_BUFS ? pn - ST_BUFS : 0); p < pn; ++p) retire(p);  // drain
   } else {
-    // ===================================== workers: operand assembly + epilogues ==============================
+    // ===================================== workers: operand conversion + epilogues ============================
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int h = (warp - 2) >> 2;       // which 32-column half of every 64-column slot this thread owns
+    const int h = (warp - 6) >> 2;       // which 32-column half of every 64-column chunk this thread owns
     const int r = 32 * q + lane;         // tile row
     const int wtid = h * 128 + r;        // 0..255
-    uint32_t fi = 0, li = 0;
+    const uint32_t st_row = sbase + OFF_ST + r * ST_STRIDE;
+    uint32_t fi = 0, li = 0, pn = 0;
     float amax = 0.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int grow = tile * TILE_M + r;
-      const bool valid = grow < R;
-      const int crow = valid ? grow : R - 1;  // clamped: out-of-range rows compute on a real row and are not stored
-      const int b = crow / ch.rows_per_sample, i = crow - b * ch.rows_per_sample;
 
-      // ---- stage 0: assemble the first A operand, chunk by chunk -------------------------------------------------
+    auto piece_read = [&](uint32_t p, float (&v)[32], bool accumulate) {  // wait for staged piece p, read my 32 floats
+      const uint32_t buf = p % ST_BUFS, use = p / ST_BUFS;
+      mbar_wait(bar_st_ready + 8 * buf, use & 1, ch.status);
+      const uint32_t a = st_row + buf * ST_BYTES;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 t = lds128(a + 16 * k);
+        if (accumulate) {
+          v[4 * k] += t.x, v[4 * k + 1] += t.y, v[4 * k + 2] += t.z, v[4 * k + 3] += t.w;
+        } else {
+          v[4 * k] = t.x, v[4 * k + 1] = t.y, v[4 * k + 2] = t.z, v[4 * k + 3] = t.w;
+        }
+      }
+    };
+    auto piece_wait = [&](uint32_t p) { mbar_wait(bar_st_ready + 8 * (p % ST_BUFS), (p / ST_BUFS) & 1, ch.status); };
+    auto piece_write = [&](uint32_t p, const float (&v)[32]) {
+      const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sts128(a + 16 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    };
+    auto piece_done = [&](uint32_t p) { mbar_arrive(bar_st_done + 8 * (p % ST_BUFS)); };
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // ---- stage 0: staged fp32 rows -> fp16 hi/lo operand chunks -----------------------------------------------
       {
         const int nk0 = ch.K0 >> 6;
-        const int w0 = ch.a0[0].width;
-        for (int c = 0; c < nk0; ++c, ++fi) {
+        for (int c = 0; c < nk0; ++c, ++fi, pn += 2) {
           const uint32_t slot = fi % A_SLOTS, n = fi / A_SLOTS;
           float v[32];
-          const int col = 64 * c + 32 * h;
-          // a0[0].width is a multiple of 32 whenever a second source follows (checked on the host)
-          if (col < w0) {
-            src_piece<false>(ch.a0[0], b, i, col, v);
-          } else if (ch.a0[1].kind != SRC_NONE && col - w0 < ch.a0[1].width) {
-            src_piece<false>(ch.a0[1], b, i, col - w0, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
+          piece_read(pn + h, v, false);
+          piece_done(pn + h);
           mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
           store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
           fence_proxy_async();
           mbar_arrive(bar_full_a + 8 * slot);
         }
       }
-
       // ---- layers -------------------------------------------------------------------------------------------------
       for (int l = 0; l < ch.n_layers; ++l, ++li) {
         const TcLayer& L = ch.layer[l];
         const uint32_t acc = li & 1, use = li >> 1;
-        const int npieces = (L.N + 63) >> 6;
+        const int N = L.N, nval = L.n_valid;
+        const int np = (N + 63) >> 6;
+        const float wsi = L.wscale_inv;
+        const float* bias = L.bias;
+        const bool has_add = L.add[0].kind != SRC_NONE;
+        const bool has_res = L.residual.kind != SRC_NONE;
+        const bool has_ro = has_res || L.out != nullptr;
         mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
         float mean = 0.f, rstd = 1.f;
         if (L.ln_g) {
-          // LayerNorm statistics over the N outputs of this row; the row is shared by two threads (h = 0, 1).
-          // Two passes over TMEM (mean, then centred second moment) like torch's CPU kernel; TMEM reads are cheap.
+          // LayerNorm statistics of this row (shared by the two threads h = 0, 1): mean, then centred second moment,
+          // both straight from TMEM (two extra TMEM passes are cheaper than holding 128 values in registers)
           float s1 = 0.f;
-          for (int s = 0; s < npieces; ++s) {
+          for (int s = 0; s < np; ++s) {
             const int c0 = 64 * s + 32 * h;
-            if (c0 >= L.N) break;
+            if (c0 >= N) break;
             float v[32];
             tmem_ld32(taddr + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f);
-              s1 += (c0 + j < L.N) ? x : 0.f;
-            }
+            for (int j = 0; j < 32; ++j)
+              s1 += (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) : 0.f;
           }
           ln_x[wtid] = s1;
           named_bar_workers();
-          mean = (s1 + ln_x[wtid ^ 128]) / (float)L.N;
+          mean = (s1 + ln_x[wtid ^ 128]) / (float)nval;
           float s2 = 0.f;
-          for (int s = 0; s < npieces; ++s) {
+          for (int s = 0; s < np; ++s) {
             const int c0 = 64 * s + 32 * h;
-            if (c0 >= L.N) break;
+            if (c0 >= N) break;
             float v[32];
             tmem_ld32(taddr + c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float x = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f) - mean;
-              s2 += (c0 + j < L.N) ? x * x : 0.f;
+              const float x = (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) - mean : 0.f;
+              s2 += x * x;
             }
           }
           ln_y[wtid] = s2;
           named_bar_workers();
-          rstd = 1.0f / sqrtf((s2 + ln_y[wtid ^ 128]) / (float)L.N + 1e-5f);
+          rstd = 1.0f / sqrtf((s2 + ln_y[wtid ^ 128]) / (float)nval + 1e-5f);
         }
-        for (int s = 0; s < npieces; ++s) {
+        for (int s = 0; s < np; ++s) {
           const int c0 = 64 * s + 32 * h;
+          // staged pieces of this chunk, in the movers' order: add(h=0), add(h=1), residual/out(h=0), residual/out(h=1)
+          const int n_h = (64 * s + 32 < N) ? 2 : 1;  // does the h = 1 half of this chunk exist?
+          uint32_t p_add = 0, p_ro = 0;
+          if (has_add) {
+            p_add = pn + h;
+            pn += n_h;
+          }
+          if (has_ro) {
+            p_ro = pn + h;
+            pn += n_h;
+          }
           float v[32];
-          if (c0 < L.N) {
+          if (c0 < N) {
             tmem_ld32(taddr + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * L.wscale_inv + (L.bias ? __ldg(L.bias + c0 + j) : 0.f);
-            if (L.add[0].kind != SRC_NONE) src_piece<true>(L.add[0], b, i, c0, v);
-            if (L.add[1].kind != SRC_NONE) src_piece<true>(L.add[1], b, i, c0, v);
+            for (int j = 0; j < 32; ++j) v[j] = (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) : 0.f;
+            if (has_add) {
+              piece_read(p_add, v, true);
+              piece_done(p_add);
+            }
             if (L.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -466,26 +628,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             if (L.ln_g) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                v[j] = (c0 + j < L.N) ? (v[j] - mean) * rstd * __ldg(L.ln_g + c0 + j) + __ldg(L.ln_b + c0 + j) : 0.f;
+                v[j] = (c0 + j < nval) ? (v[j] - mean) * rstd * __ldg(L.ln_g + c0 + j) + __ldg(L.ln_b + c0 + j) : 0.f;
             }
-            if (L.residual.kind != SRC_NONE) src_piece<true>(L.residual, b, i, c0, v);
-            if (L.out && valid && c0 < L.out_cols) {
-              float* o = L.out + (size_t)grow * L.ldo + c0;
-              if (c0 + 32 <= L.out_cols && vec4_ok(L.out, L.ldo, c0)) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < L.out_cols) o[j] = v[j];
-              }
+            if (has_ro) {
+              if (has_res) piece_read(p_ro, v, true);
+              else piece_wait(p_ro);
+              if (L.out) piece_write(p_ro, v);  // in place: each thread overwrites exactly the bytes it read
+              piece_done(p_ro);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (L.feeds_next) {  // publish this 64-column slot of the next operand as soon as both halves are written
+          if (L.feeds_next) {  // publish this 64-column chunk of the next operand as soon as both halves are written
             const uint32_t f = fi + s, slot = f % A_SLOTS, n = f / A_SLOTS;
             mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
             store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
@@ -493,7 +648,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             mbar_arrive(bar_full_a + 8 * slot);
           }
         }
-        if (L.feeds_next) fi += npieces;
+        if (L.feeds_next) fi += np;
         tc_fence_before();
         mbar_arrive(bar_empty_d + 8 * acc);  // this thread no longer reads the accumulator
       }
@@ -585,12 +740,15 @@ cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream) {
   if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 31)) return cudaErrorInvalidValue;
   for (int l = 0; l < ch.n_layers; ++l) {
     const TcLayer& L = ch.layer[l];
-    if (!L.Wp || (L.K & 63) || (L.N & 31) || L.N > 256 || L.N <= 0) return cudaErrorInvalidValue;
+    if (!L.Wp || (L.K & 63) || (L.N & 15) || L.N > 256 || L.N <= 0 || L.n_valid <= 0 || L.n_valid > L.N) return cudaErrorInvalidValue;
+    if (L.feeds_next && (L.N & 63)) return cudaErrorInvalidValue;
+    if (L.ln_g && L.add[0].kind != SRC_NONE) return cudaErrorInvalidValue;   // addends are applied before ReLU, not before LayerNorm
+    if (L.add[0].kind == SRC_NONE && L.add[1].kind != SRC_NONE) return cudaErrorInvalidValue;
     if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
     if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;
-    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next)) return cudaErrorInvalidValue;
+    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next || L.K > 64 * A_SLOTS)) return cudaErrorInvalidValue;  // the whole operand must still be resident
   }
-  const int tiles = (int)((R + TILE_M - 1) / TILE_M);
+  const int tiles = ((ch.rows_per_sample + TILE_M - 1) / TILE_M) * ch.batch;
   const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
   gw_chain_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
   count_launch();
