@@ -53,6 +53,7 @@ _SIGNATURES = {
     "gw_decoder_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "gw_latent_edge_features": (ctypes.c_int, [_vp, _vp, _vp]),
     "gw_plan_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    "gw_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "gw_timing_enable": (ctypes.c_int, [_vp, _i32]),
     "gw_timing_num_tags": (_i32, []),
     "gw_timing_tag_name": (ctypes.c_char_p, [_i32]),
@@ -235,6 +236,11 @@ class Plan:
             raise RuntimeError(f"libgwb200 device status {v.value}: " + ("activation outside the fp16 range in precision 'fp32' (use 'fp32_simt'); " if v.value & 1 else "")
                                + ("pipeline timeout; " if v.value & 2 else "") + ("shared memory misaligned" if v.value & 4 else ""))
         return 0
+
+    def debug_words(self):
+        arr = (_i32 * 64)()
+        self.lib.gw_plan_debug(self.handle, arr)
+        return list(arr)
 
     def timing_enable(self, on: bool):
         _check(self.lib.gw_timing_enable(self.handle, 1 if on else 0))

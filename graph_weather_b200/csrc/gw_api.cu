@@ -125,7 +125,8 @@ struct gw_plan {
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
-  DevBuf<int32_t> tc_status;
+  int32_t* tc_status_host = nullptr;  // 16 words, pinned + mapped: stays readable by the host after a device trap
+  int32_t* tc_status_dev = nullptr;
   TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node, tc_dec_out;
   bool tc_dec_out_ok = false;  // node_decoder fits the chain kernel (hidden_dec multiple of 64, 2 hidden layers)
   DevBuf<float> agg_mesh;     // [chunk*n_mesh, De] encoder aggregation (segment sums)
@@ -220,7 +221,7 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
 
 static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
-  ch.status = p->tc_status.p;
+  ch.status = p->tc_status_dev;
   cudaError_t e;
   {
     TimedLaunch t(p, st);
@@ -900,7 +901,6 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->xbuf0.alloc(B * d.n_mesh * Dn) | p->xbuf1.alloc(B * d.n_mesh * Dn);
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
-  rc |= p->tc_status.alloc(1);
   rc |= p->agg_mesh.alloc(chunk * d.n_mesh * De);
   if (rc) {
     std::string keep = gw::g_err;
@@ -909,7 +909,9 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
     return 1;
   }
   GW_CUDA(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
-  GW_CUDA(cudaMemset(p->tc_status.p, 0, sizeof(int32_t)));
+  GW_CUDA(cudaHostAlloc((void**)&p->tc_status_host, 64 * sizeof(int32_t), cudaHostAllocMapped));
+  std::memset(p->tc_status_host, 0, 64 * sizeof(int32_t));
+  GW_CUDA(cudaHostGetDevicePointer((void**)&p->tc_status_dev, p->tc_status_host, 0));
   p->n_in_cur = d.n_in;
   *out_plan = p;
   return 0;
@@ -923,7 +925,8 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
-  p->tc_packed.release(), p->tc_absmax.release(), p->tc_status.release(), p->agg_mesh.release();
+  p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release();
+  if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;
@@ -1058,11 +1061,22 @@ int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {
 
 int gw_plan_status(gw_plan* p, int32_t* status_out, void* stream) {
   GW_CHECK(p && status_out, "null argument");
-  GW_CUDA(cudaSetDevice(p->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  GW_CUDA(cudaMemcpyAsync(status_out, p->tc_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  GW_CUDA(cudaStreamSynchronize(st));
-  if (*status_out) GW_CUDA(cudaMemsetAsync(p->tc_status.p, 0, sizeof(int32_t), st));
+  cudaSetDevice(p->device);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  volatile int32_t* h = p->tc_status_host;
+  *status_out = h[0];
+  if (e != cudaSuccess) {  // e.g. a trap: report what the device recorded (the block is host memory, still readable)
+    gw::set_error(std::string("device fault: ") + cudaGetErrorString(e) + "; status word " + std::to_string(h[0]) +
+                  " (per-warp wait records: gw_plan_debug)");
+    return 1;
+  }
+  if (h[0]) h[0] = 0;
+  return 0;
+}
+
+int gw_plan_debug(gw_plan* p, int32_t* out16) {
+  GW_CHECK(p && out16, "null argument");
+  for (int i = 0; i < 64; ++i) out16[i] = ((volatile int32_t*)p->tc_status_host)[i];
   return 0;
 }
 

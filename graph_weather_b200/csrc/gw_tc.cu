@@ -17,12 +17,14 @@
 // CTA layout (448 threads, one persistent CTA per SM):
 //   warp 0   lane 0: weight producer -- streams pre-swizzled weight panels global->smem with cp.async.bulk (UBLKCP)
 //   warp 1   lane 0: MMA issuer      -- tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256, K=16 per instruction
-//   warps 2-5      : 128 movers      -- ALL global row traffic: gather / stream / CSR segment-sum rows into padded
-//                                       fp32 staging pieces (cp.async 16 B or vector loads, 8 lanes per 128 B row line)
-//                                       and coalesced stores of finished rows out of staging
-//   warps 6-13     : 256 workers     -- thread (q,lane,h) owns tile row 32q+lane and the 32-column pieces 64s+32h; they
-//                                       convert staged rows to fp16 hi/lo operands and run every epilogue from TMEM;
-//                                       they touch TMEM and shared memory only
+//   warps 2-7      : 192 movers      -- ALL global row traffic, in three groups of 64 that each own one staging buffer:
+//                                       gather / stream / CSR segment-sum rows into padded fp32 staging pieces
+//                                       (cp.async 16 B or index-hoisted vector loads, 8 lanes per 128 B row line) and
+//                                       coalesced stores of finished rows out of staging
+//   warps 8-15     : 256 workers     -- thread (q,lane,h) owns tile row 32q+lane (= TMEM lane) and the 32-column pieces
+//                                       64s+32h; they convert staged rows to fp16 hi/lo operands and run every epilogue
+//                                       from TMEM (bias, addend, ReLU, LayerNorm, residual) touching only TMEM and
+//                                       shared memory (per-layer bias / gamma / beta are staged in shared memory once)
 // Shared memory: 2 A slots x [128 x 64] (hi|lo) = 64 KB, 3 weight stages x [256 x 64] = 96 KB, 3 staging pieces
 // [128 x 32] fp32 = 54 KB, mbarriers.  TMEM: 512 columns = two 128x256 fp32 accumulators, so the MMAs of layer l+1
 // overlap the epilogue of layer l chunk by chunk, and the movers prefetch the next tile during the last epilogue.
@@ -45,8 +47,10 @@ constexpr int A_SLOT_BYTES = 2 * A_HALF_BYTES;  // hi | lo
 constexpr int B_STAGE_BYTES = 256 * 128;        // [256 rows x 64 halfs], hi OR lo panel
 constexpr int ST_STRIDE = 144;                  // staging row: 32 fp32 + 16 B pad (conflict-free 16-byte row access)
 constexpr int ST_BYTES = TILE_M * ST_STRIDE;    // one [128 rows x 32 cols] fp32 piece
-constexpr int NUM_MOVERS = 128;
-constexpr int NUM_WORKERS = 256;
+constexpr int NUM_MOVERS = 192;   // three groups of 64; group g owns staging buffer g (pieces p with p % 3 == g)
+constexpr int MOVER_GROUP = 64;
+constexpr int NUM_WORKERS = 256;  // thread (row, h): tile row = TMEM lane, h = which 32-column half of each 64-column chunk
+constexpr int PAR_LAYERS = 6;     // per-layer parameter rows staged in shared memory (bias; LayerNorm gamma/beta for <= 2 layers)
 constexpr int NUM_THREADS = 64 + NUM_MOVERS + NUM_WORKERS;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
@@ -54,7 +58,9 @@ constexpr int OFF_ST = OFF_B + B_STAGES * B_STAGE_BYTES;
 constexpr int OFF_BAR = OFF_ST + ST_BUFS * ST_BYTES;
 constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4 + 2 * ST_BUFS;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr int OFF_LN = OFF_TMEM + 16;
+constexpr int OFF_PAR = OFF_TMEM + 16;                       // float bias[PAR_LAYERS][256]
+constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;         // float gamma_beta[2][2][256]
+constexpr int OFF_LN = OFF_LNP + 4 * 1024;                   // float ln_x[256], ln_y[256]: row statistics exchange
 constexpr int SMEM_BYTES = OFF_LN + 2 * NUM_WORKERS * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
@@ -85,16 +91,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  After ~4 s the CTA flags status bit 1 and traps.
+// Bounded wait: a protocol bug must not hang the GPU.  After ~4 s the thread records which barrier it was waiting on in the
+// (host-mapped) status block -- word 0 bit 1, words 1..5 = barrier byte offset, parity, thread, block, role tag -- and traps.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int32_t* status) {
+  if (status) {
+    extern __shared__ __align__(1024) uint8_t smem_dbg[];
+    atomicOr(status, 2);
+    const int w = threadIdx.x >> 5;  // one record per warp: {barrier byte offset in smem, parity, block}
+    status[4 + 3 * w + 0] = (int32_t)(bar - (uint32_t)__cvta_generic_to_shared(smem_dbg));
+    status[4 + 3 * w + 1] = (int32_t)parity;
+    status[4 + 3 * w + 2] = (int32_t)blockIdx.x;
+  }
+  __threadfence_system();
+  // give the other warps of this CTA time to record their own stuck waits before the context dies
+  for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
-      if (status) atomicOr(status, 2);
-      __threadfence_system();
-      __trap();
-    }
+    if (clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity, status);
+  }
+}
+// Same, for threads that expect to wait long (movers): sleep between polls so they do not steal issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int32_t* status) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if (clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity, status);
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -286,8 +312,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
   const uint32_t bar_st_ready = bar_empty_d + 16;           // [ST_BUFS] movers -> workers: staging piece filled / free
   const uint32_t bar_st_done = bar_st_ready + 8 * ST_BUFS;  // [ST_BUFS] workers (one h group) -> movers: piece consumed / produced
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
-  float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
-  float* ln_y = ln_x + NUM_WORKERS;
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {  // SWIZZLE_128B operand tiles must be 1 KB aligned
@@ -297,13 +321,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
     for (int i = 0; i < A_SLOTS; ++i) mbar_init(bar_full_a + 8 * i, NUM_WORKERS), mbar_init(bar_empty_a + 8 * i, 1);
     for (int i = 0; i < B_STAGES; ++i) mbar_init(bar_full_b + 8 * i, 1), mbar_init(bar_empty_b + 8 * i, 1);
     for (int i = 0; i < 2; ++i) mbar_init(bar_full_d + 8 * i, 1), mbar_init(bar_empty_d + 8 * i, NUM_WORKERS);
-    for (int i = 0; i < ST_BUFS; ++i) mbar_init(bar_st_ready + 8 * i, NUM_MOVERS), mbar_init(bar_st_done + 8 * i, NUM_WORKERS / 2);
+    for (int i = 0; i < ST_BUFS; ++i) mbar_init(bar_st_ready + 8 * i, MOVER_GROUP), mbar_init(bar_st_done + 8 * i, NUM_WORKERS);
     fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // per-layer column parameters -> shared memory (zero beyond n_valid), read by the epilogues as broadcast LDS.128
+    float* par = reinterpret_cast<float*>(smem + OFF_PAR);
+    float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
+    int ln_slot = 0;
+    for (int l = 0; l < ch.n_layers; ++l) {
+      const TcLayer& L = ch.layer[l];
+      for (int c = threadIdx.x; c < 256; c += NUM_THREADS) par[l * 256 + c] = (L.bias && c < L.n_valid) ? __ldg(L.bias + c) : 0.f;
+      if (L.ln_g) {
+        for (int c = threadIdx.x; c < 256; c += NUM_THREADS) {
+          lnp[(ln_slot * 2 + 0) * 256 + c] = (c < L.n_valid) ? __ldg(L.ln_g + c) : 0.f;
+          lnp[(ln_slot * 2 + 1) * 256 + c] = (c < L.n_valid) ? __ldg(L.ln_b + c) : 0.f;
+        }
+        ++ln_slot;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -387,72 +427,148 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 8) {
     // ===================================== movers ==============================================================
-    // Thread (rsub, ck) moves the 16-byte group ck of rows rsub, rsub+16, ..: 8 lanes cover one 128-byte row line.
-    const int mt = threadIdx.x - 64;
+    // Group g (64 threads) owns staging buffer g and fills the pieces p with p % 3 == g.  Thread (rsub, ck) moves the
+    // 16-byte group ck of rows rsub, rsub+8, ..: 8 lanes cover one 128-byte row line, a warp covers 4 rows per access.
+    const int mgroup = (warp - 2) >> 1;
+    const int mt = (threadIdx.x - 64) & (MOVER_GROUP - 1);
     const int rsub = mt >> 3, ck = mt & 7;
-    uint32_t pn = 0;
-    Retire ring[ST_BUFS];
-#pragma unroll
-    for (int i = 0; i < ST_BUFS; ++i) ring[i].out = nullptr;
+    const uint32_t st = sbase + OFF_ST + mgroup * ST_BYTES + ck * 16;
+    const uint32_t bar_ready = bar_st_ready + 8 * mgroup, bar_done = bar_st_done + 8 * mgroup;
+    uint32_t pn = 0, my_use = 0;
+    Retire prev;  // my previous piece (same buffer): must be retired before the buffer is refilled
+    prev.out = nullptr, prev.ldo = 0, prev.out_cols = 0, prev.c0 = 0, prev.nvalid = 0;
 
-    auto retire = [&](uint32_t p) {  // piece p: wait until its workers are done with it, then store its output rows
-      const uint32_t buf = p % ST_BUFS, use = p / ST_BUFS;
-      mbar_wait(bar_st_done + 8 * buf, use & 1, ch.status);
-      const Retire rt = ring[buf];
-      if (rt.out) {
-        const uint32_t st = sbase + OFF_ST + buf * ST_BYTES + ck * 16;
-        const int col = rt.c0 + 4 * ck;
-        const bool vec = vec4_ok(rt.out, rt.ldo, col) && col + 4 <= rt.out_cols;
+    auto retire = [&]() {  // wait until the workers are done with my previous piece, then store its output rows
+      mbar_wait_backoff(bar_done, (my_use - 1) & 1, ch.status);
+      if (prev.out) {
+        const int col = prev.c0 + 4 * ck;
+        const bool vec = vec4_ok(prev.out, prev.ldo, col) && col + 4 <= prev.out_cols;
+        if (col < prev.out_cols) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rsub + 16 * j;
-          if (r < rt.nvalid && col < rt.out_cols) {
-            const float4 v = lds128(st + r * ST_STRIDE);
-            float* o = rt.out + (size_t)r * rt.ldo + col;
-            if (vec) {
-              *reinterpret_cast<float4*>(o) = v;
-            } else {
-              o[0] = v.x;
-              if (col + 1 < rt.out_cols) o[1] = v.y;
-              if (col + 2 < rt.out_cols) o[2] = v.z;
-              if (col + 3 < rt.out_cols) o[3] = v.w;
+          for (int j = 0; j < 16; ++j) {
+            const int r = rsub + 8 * j;
+            if (r < prev.nvalid) {
+              const float4 v = lds128(st + r * ST_STRIDE);
+              float* o = prev.out + (size_t)r * prev.ldo + col;
+              if (vec) {
+                *reinterpret_cast<float4*>(o) = v;
+              } else {
+                o[0] = v.x;
+                if (col + 1 < prev.out_cols) o[1] = v.y;
+                if (col + 2 < prev.out_cols) o[2] = v.z;
+                if (col + 3 < prev.out_cols) o[3] = v.w;
+              }
             }
           }
         }
       }
     };
-    // piece: fill staging from up to two sources (summed); s0 may be SRC_NONE (output-only piece: just hand the buffer over)
-    auto piece = [&](const RowSrc& s0, const RowSrc& s1, int c, int bs, int i0, int nvalid, const Retire& rt) {
-      const uint32_t buf = pn % ST_BUFS;
-      if (pn >= ST_BUFS) retire(pn - ST_BUFS);
-      ring[buf] = rt;
-      const uint32_t st = sbase + OFF_ST + buf * ST_BYTES + ck * 16;
-      const uint32_t bar = bar_st_ready + 8 * buf;
-      const int col = c + 4 * ck;
-      if (s0.kind == SRC_NONE) {
-        mbar_arrive(bar);
-      } else if (s1.kind == SRC_NONE && is_simple(s0.kind) && vec4_ok(s0.base, s0.ld, s0.col0 + c) && c + 32 <= s0.width) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rsub + 16 * j;
-          const int i = i0 + min(r, nvalid - 1);  // rows past the end of the sample re-read the last valid row
-          cp_async16(st + r * ST_STRIDE, simple_row(s0, bs, i) + col);
-        }
-        cp_async_arrive_noinc(bar);
-      } else {
-#pragma unroll 2
-        for (int j = 0; j < 8; ++j) {
-          const int r = rsub + 16 * j;
-          const int i = i0 + min(r, nvalid - 1);
-          float4 v = src_load4(s0, bs, i, col);
-          if (s1.kind != SRC_NONE) v = add4(v, src_load4(s1, bs, i, col));
-          sts128(st + r * ST_STRIDE, v);
-        }
-        mbar_arrive(bar);
+    // One staging piece: filled from up to two sources (summed); s0 == SRC_NONE is an output-only piece (the buffer is
+    // just handed to the workers).  Every group and the workers enumerate the pieces identically.
+    auto do_piece = [&](const RowSrc& s0, const RowSrc& s1, int c, int bs, int i0, int nvalid, const Retire& rt) {
+      if (pn % ST_BUFS != (uint32_t)mgroup) {
+        ++pn;
+        return;
       }
       ++pn;
+      if (my_use > 0) retire();
+      prev = rt;
+      ++my_use;
+      const int col = c + 4 * ck;
+      if (s0.kind == SRC_NONE) {
+        mbar_arrive(bar_ready);
+        return;
+      }
+      const bool al0 = vec4_ok(s0.base, s0.ld, s0.col0 + c) && c + 32 <= s0.width;
+      if (s1.kind == SRC_NONE && is_simple(s0.kind) && al0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float* rp[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rp[j] = simple_row(s0, bs, i0 + min(rsub + 8 * (8 * half + j), nvalid - 1));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp_async16(st + (rsub + 8 * (8 * half + j)) * ST_STRIDE, rp[j] + col);
+        }
+        cp_async_arrive_noinc(bar_ready);
+      } else if (is_simple(s0.kind) && is_simple(s1.kind) && al0 && vec4_ok(s1.base, s1.ld, s1.col0 + c) && c + 32 <= s1.width) {
+        // sum of two gathered / streamed rows (P_s[src] + P_d[dst]): all index loads, then all data loads
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float *rp[8], *rq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = i0 + min(rsub + 8 * (8 * half + j), nvalid - 1);
+            rp[j] = simple_row(s0, bs, i), rq[j] = simple_row(s1, bs, i);
+          }
+          float4 v[8], w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(rp[j] + col));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(rq[j] + col));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(st + (rsub + 8 * (8 * half + j)) * ST_STRIDE, add4(v[j], w[j]));
+        }
+        mbar_arrive(bar_ready);
+      } else if (s0.kind == SRC_GATHER_BCAST_RELU && s1.kind == SRC_NONE && al0 && vec4_ok(s0.base2, s0.ld2, c)) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float* rp[8];
+          float4 v[8], w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = i0 + min(rsub + 8 * (8 * half + j), nvalid - 1);
+            rp[j] = s0.base + ((size_t)bs * s0.src_rows + __ldg(s0.idx + i)) * s0.ld + s0.col0;
+            w[j] = __ldg(reinterpret_cast<const float4*>(s0.base2 + (size_t)i * s0.ld2 + col));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(rp[j] + col));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = add4(v[j], w[j]);
+            sts128(st + (rsub + 8 * (8 * half + j)) * ST_STRIDE,
+                   make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f)));
+          }
+        }
+        mbar_arrive(bar_ready);
+      } else if (s0.kind == SRC_SEGSUM && s1.kind == SRC_NONE && !s0.perm && al0) {
+        // CSR segment sums over contiguous edge rows (in-degree 6/7 on the mesh and decoder graphs)
+        const float* tb = s0.base + (size_t)bs * s0.src_rows * s0.ld + s0.col0 + col;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int j0[8], j1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = i0 + min(rsub + 8 * (8 * half + j), nvalid - 1);
+            j0[j] = __ldg(s0.ptr + i), j1[j] = __ldg(s0.ptr + i + 1);
+          }
+#pragma unroll 2
+          for (int j = 0; j < 8; ++j) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int e = j0[j];
+            for (; e + 4 <= j1[j]; e += 4) {  // four rows in flight, summed left to right (reference order)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(tb + (size_t)e * s0.ld));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(tb + (size_t)(e + 1) * s0.ld));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(tb + (size_t)(e + 2) * s0.ld));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(tb + (size_t)(e + 3) * s0.ld));
+              acc = add4(add4(add4(add4(acc, a0), a1), a2), a3);
+            }
+            for (; e < j1[j]; ++e) acc = add4(acc, __ldg(reinterpret_cast<const float4*>(tb + (size_t)e * s0.ld)));
+            sts128(st + (rsub + 8 * (8 * half + j)) * ST_STRIDE, acc);
+          }
+        }
+        mbar_arrive(bar_ready);
+      } else {  // generic (unaligned / partial-width / permuted) path
+#pragma unroll 2
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + min(rsub + 8 * j, nvalid - 1);
+          float4 v = src_load4(s0, bs, i, col);
+          if (s1.kind != SRC_NONE) v = add4(v, src_load4(s1, bs, i, col));
+          sts128(st + (rsub + 8 * j) * ST_STRIDE, v);
+        }
+        mbar_arrive(bar_ready);
+      }
     };
 
     const RowSrc none;
@@ -467,13 +583,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         for (int h = 0; h < 2; ++h) {
           const int col = 64 * c + 32 * h;
           if (col < w0) {
-            piece(ch.a0[0], none, col, bs, i0, nvalid, no_out);
+            do_piece(ch.a0[0], none, col, bs, i0, nvalid, no_out);
           } else if (ch.a0[1].kind != SRC_NONE && col - w0 < ch.a0[1].width) {
-            piece(ch.a0[1], none, col - w0, bs, i0, nvalid, no_out);
+            do_piece(ch.a0[1], none, col - w0, bs, i0, nvalid, no_out);
           } else {  // zero padding of K0: a source of width 0 reads as zeros
             RowSrc z = ch.a0[0];
             z.width = 0, z.kind = SRC_STREAM;
-            piece(z, z, col, bs, i0, nvalid, no_out);
+            do_piece(z, z, col, bs, i0, nvalid, no_out);
           }
         }
       }
@@ -487,7 +603,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
           if (has_add)
             for (int h = 0; h < 2; ++h) {
               const int c0 = 64 * s + 32 * h;
-              if (c0 < L.N) piece(L.add[0], L.add[1], c0, bs, i0, nvalid, no_out);
+              if (c0 < L.N) do_piece(L.add[0], L.add[1], c0, bs, i0, nvalid, no_out);
             }
           if (has_ro)
             for (int h = 0; h < 2; ++h) {
@@ -498,27 +614,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
                   rt.out = L.out + ((size_t)bs * rows + i0) * L.ldo;
                   rt.ldo = L.ldo, rt.out_cols = L.out_cols, rt.c0 = c0;
                 }
-                piece(L.residual, none, c0, bs, i0, nvalid, rt);
+                do_piece(L.residual, none, c0, bs, i0, nvalid, rt);
               }
             }
         }
       }
     }
-    for (uint32_t p = (pn > ST_BUFS ? pn - ST_BUFS : 0); p < pn; ++p) retire(p);  // drain
+    if (my_use > 0) retire();  // drain my last piece
   } else {
     // ===================================== workers: operand conversion + epilogues ============================
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int h = (warp - 6) >> 2;       // which 32-column half of every 64-column chunk this thread owns
-    const int r = 32 * q + lane;         // tile row
-    const int wtid = h * 128 + r;        // 0..255
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int h = (warp - 8) >> 2;   // which 32-column half of every 64-column chunk this thread owns
+    const int r = 32 * q + lane;     // tile row == TMEM lane
+    const int wtid = h * 128 + r;
     const uint32_t st_row = sbase + OFF_ST + r * ST_STRIDE;
+    const uint32_t par_base = sbase + OFF_PAR, lnp_base = sbase + OFF_LNP;
+    float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
+    float* ln_y = ln_x + NUM_WORKERS;
     uint32_t fi = 0, li = 0, pn = 0;
     float amax = 0.f;
 
+    auto piece_wait = [&](uint32_t p) { mbar_wait(bar_st_ready + 8 * (p % ST_BUFS), (p / ST_BUFS) & 1, ch.status); };
     auto piece_read = [&](uint32_t p, float (&v)[32], bool accumulate) {  // wait for staged piece p, read my 32 floats
-      const uint32_t buf = p % ST_BUFS, use = p / ST_BUFS;
-      mbar_wait(bar_st_ready + 8 * buf, use & 1, ch.status);
-      const uint32_t a = st_row + buf * ST_BYTES;
+      piece_wait(p);
+      const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float4 t = lds128(a + 16 * k);
@@ -529,13 +648,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
     };
-    auto piece_wait = [&](uint32_t p) { mbar_wait(bar_st_ready + 8 * (p % ST_BUFS), (p / ST_BUFS) & 1, ch.status); };
     auto piece_write = [&](uint32_t p, const float (&v)[32]) {
       const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
 #pragma unroll
       for (int k = 0; k < 8; ++k) sts128(a + 16 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
     };
     auto piece_done = [&](uint32_t p) { mbar_arrive(bar_st_done + 8 * (p % ST_BUFS)); };
+    // A staging buffer serves pieces of either half-group in turn.  The half that does not own piece p still waits for
+    // its ready phase and arrives on its done barrier ("observes" it), so that every worker sees every phase of every
+    // barrier in order and a buffer is never refilled while some warp has yet to pass the previous phase (a parity
+    // wait would otherwise be ambiguous by two phases).
+    auto piece_observe = [&](uint32_t p) {
+      piece_wait(p);
+      piece_done(p);
+    };
+    // v = acc * wscale_inv + bias for 32 columns starting at c0 (bias row lives in shared memory, zero past n_valid)
+    auto scale_bias = [&](float (&v)[32], float wsi, uint32_t bias_s) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 b4 = lds128(bias_s + 16 * k);
+        v[4 * k] = fmaf(v[4 * k], wsi, b4.x), v[4 * k + 1] = fmaf(v[4 * k + 1], wsi, b4.y);
+        v[4 * k + 2] = fmaf(v[4 * k + 2], wsi, b4.z), v[4 * k + 3] = fmaf(v[4 * k + 3], wsi, b4.w);
+      }
+    };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       // ---- stage 0: staged fp32 rows -> fp16 hi/lo operand chunks -----------------------------------------------
@@ -544,8 +679,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         for (int c = 0; c < nk0; ++c, ++fi, pn += 2) {
           const uint32_t slot = fi % A_SLOTS, n = fi / A_SLOTS;
           float v[32];
+          // every worker observes every piece's ready phase in order (a buffer is reused by pieces of either half;
+          // skipping a phase would let a parity wait succeed one use early); only the owning half consumes the piece
+          if (h == 1) piece_observe(pn);
           piece_read(pn + h, v, false);
           piece_done(pn + h);
+          if (h == 0) piece_observe(pn + 1);
           mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
           store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
           fence_proxy_async();
@@ -553,32 +692,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
       // ---- layers -------------------------------------------------------------------------------------------------
+      int ln_slot = 0;
       for (int l = 0; l < ch.n_layers; ++l, ++li) {
         const TcLayer& L = ch.layer[l];
         const uint32_t acc = li & 1, use = li >> 1;
         const int N = L.N, nval = L.n_valid;
         const int np = (N + 63) >> 6;
         const float wsi = L.wscale_inv;
-        const float* bias = L.bias;
+        const uint32_t bias_s = par_base + l * 1024;
         const bool has_add = L.add[0].kind != SRC_NONE;
         const bool has_res = L.residual.kind != SRC_NONE;
-        const bool has_ro = has_res || L.out != nullptr;
+        const bool has_out = L.out != nullptr;
+        const bool has_ro = has_res || has_out;
+        const bool relu = L.relu != 0, has_ln = L.ln_g != nullptr, feeds = L.feeds_next != 0;
+        const uint32_t g_s = lnp_base + (ln_slot * 2) * 1024, b_s = g_s + 1024;
+        if (has_ln) ++ln_slot;
         mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
         float mean = 0.f, rstd = 1.f;
-        if (L.ln_g) {
+        if (has_ln) {
           // LayerNorm statistics of this row (shared by the two threads h = 0, 1): mean, then centred second moment,
-          // both straight from TMEM (two extra TMEM passes are cheaper than holding 128 values in registers)
+          // like torch's CPU kernel, both straight from TMEM (cheaper than holding 128 values in registers).
+          // Columns >= n_valid contribute exactly 0 to both sums only if N == n_valid, which the host guarantees for LN.
           float s1 = 0.f;
           for (int s = 0; s < np; ++s) {
             const int c0 = 64 * s + 32 * h;
             if (c0 >= N) break;
             float v[32];
             tmem_ld32(taddr + c0, v);
+            scale_bias(v, wsi, bias_s + 4 * c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              s1 += (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) : 0.f;
+            for (int j = 0; j < 32; ++j) s1 += v[j];
           }
           ln_x[wtid] = s1;
           named_bar_workers();
@@ -589,10 +734,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             if (c0 >= N) break;
             float v[32];
             tmem_ld32(taddr + c0, v);
+            scale_bias(v, wsi, bias_s + 4 * c0);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float x = (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) - mean : 0.f;
-              s2 += x * x;
+              const float x = v[j] - mean;
+              s2 = fmaf(x, x, s2);
             }
           }
           ln_y[wtid] = s2;
@@ -602,45 +748,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         for (int s = 0; s < np; ++s) {
           const int c0 = 64 * s + 32 * h;
           // staged pieces of this chunk, in the movers' order: add(h=0), add(h=1), residual/out(h=0), residual/out(h=1)
-          const int n_h = (64 * s + 32 < N) ? 2 : 1;  // does the h = 1 half of this chunk exist?
-          uint32_t p_add = 0, p_ro = 0;
-          if (has_add) {
-            p_add = pn + h;
-            pn += n_h;
-          }
-          if (has_ro) {
-            p_ro = pn + h;
-            pn += n_h;
-          }
+          const int n_h = (64 * s + 32 < N) ? 2 : 1;
+          const uint32_t p_add = pn + h;
+          if (has_add) pn += n_h;
+          const uint32_t p_ro = pn + h;
+          if (has_ro) pn += n_h;
           float v[32];
           if (c0 < N) {
             tmem_ld32(taddr + c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (c0 + j < nval) ? v[j] * wsi + (bias ? __ldg(bias + c0 + j) : 0.f) : 0.f;
+            scale_bias(v, wsi, bias_s + 4 * c0);
             if (has_add) {
+              if (h == 1) piece_observe(p_add - 1);
               piece_read(p_add, v, true);
               piece_done(p_add);
+              if (h == 0 && n_h == 2) piece_observe(p_add + 1);
             }
-            if (L.relu) {
+            if (relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (L.ln_g) {
+            if (has_ln) {
+              const float nm = -mean * rstd;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 g4 = lds128(g_s + 4 * c0 + 16 * k), e4 = lds128(b_s + 4 * c0 + 16 * k);
+                v[4 * k] = fmaf(fmaf(v[4 * k], rstd, nm), g4.x, e4.x);
+                v[4 * k + 1] = fmaf(fmaf(v[4 * k + 1], rstd, nm), g4.y, e4.y);
+                v[4 * k + 2] = fmaf(fmaf(v[4 * k + 2], rstd, nm), g4.z, e4.z);
+                v[4 * k + 3] = fmaf(fmaf(v[4 * k + 3], rstd, nm), g4.w, e4.w);
+              }
+            }
+            if (nval < N) {  // padded output columns (e.g. 78 of 80) must stay exactly zero
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                v[j] = (c0 + j < nval) ? (v[j] - mean) * rstd * __ldg(L.ln_g + c0 + j) + __ldg(L.ln_b + c0 + j) : 0.f;
+                if (c0 + j >= nval) v[j] = 0.f;
             }
             if (has_ro) {
+              if (h == 1) piece_observe(p_ro - 1);
               if (has_res) piece_read(p_ro, v, true);
               else piece_wait(p_ro);
-              if (L.out) piece_write(p_ro, v);  // in place: each thread overwrites exactly the bytes it read
+              if (has_out) piece_write(p_ro, v);  // in place: each thread overwrites exactly the bytes it read
               piece_done(p_ro);
+              if (h == 0 && n_h == 2) piece_observe(p_ro + 1);
             }
-          } else {
+          } else {  // this half of the chunk does not exist (N not a multiple of 64): still observe the other half's pieces
+            if (has_add) piece_observe(p_add - 1);
+            if (has_ro) piece_observe(p_ro - 1);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (L.feeds_next) {  // publish this 64-column chunk of the next operand as soon as both halves are written
+          if (feeds) {  // publish this 64-column chunk of the next operand as soon as both halves are written
             const uint32_t f = fi + s, slot = f % A_SLOTS, n = f / A_SLOTS;
             mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
             store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
@@ -648,7 +805,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             mbar_arrive(bar_full_a + 8 * slot);
           }
         }
-        if (L.feeds_next) fi += np;
+        if (feeds) fi += np;
         tc_fence_before();
         mbar_arrive(bar_empty_d + 8 * acc);  // this thread no longer reads the accumulator
       }
@@ -736,13 +893,15 @@ cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream) {
   const long long R = (long long)ch.rows_per_sample * ch.batch;
   if (R <= 0 || ch.n_layers <= 0) return cudaSuccess;
   // structural requirements of the kernel
-  if (ch.n_layers > TC_MAX_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
+  if (ch.n_layers > PAR_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
+  int n_ln = 0;
   if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 31)) return cudaErrorInvalidValue;
   for (int l = 0; l < ch.n_layers; ++l) {
     const TcLayer& L = ch.layer[l];
     if (!L.Wp || (L.K & 63) || (L.N & 15) || L.N > 256 || L.N <= 0 || L.n_valid <= 0 || L.n_valid > L.N) return cudaErrorInvalidValue;
     if (L.feeds_next && (L.N & 63)) return cudaErrorInvalidValue;
     if (L.ln_g && L.add[0].kind != SRC_NONE) return cudaErrorInvalidValue;   // addends are applied before ReLU, not before LayerNorm
+    if (L.ln_g && (L.n_valid != L.N || ++n_ln > 2)) return cudaErrorInvalidValue;
     if (L.add[0].kind == SRC_NONE && L.add[1].kind != SRC_NONE) return cudaErrorInvalidValue;
     if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
     if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;

@@ -123,6 +123,9 @@ int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
  * bit 0: an activation left the fp16 range in GW_PREC_FP32_TC (results invalid: rerun with GW_PREC_FP32_SIMT);
  * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment.  Non-zero must be treated as failure. */
 int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
+/* Raw copy of the plan's 64-word host-mapped status block (no CUDA call: usable after a device fault):
+ * word 0 = status flags; words 4+3w.. = {barrier byte offset, parity, block} of the wait warp w timed out on. */
+int gw_plan_debug(gw_plan* plan, int32_t* out64);
 
 /* Per-launch device timing for bench.py's live roofline measurement.  When enabled, every kernel this library
  * launches for the plan is bracketed by a cudaEvent pair recorded on the launching stream and attributed to a kernel

@@ -63,4 +63,23 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception as e:  # after a device trap the host-mapped status block still tells which barrier timed out
+        import gc
+
+        from graph_weather_b200 import _capi
+
+        print("FAILED:", str(e).splitlines()[0])
+        for o in gc.get_objects():
+            if isinstance(o, _capi.Plan) and o.handle.value:
+                w = o.debug_words()
+                if w[0]:
+                    names = ["full_a0", "full_a1", "empty_a0", "empty_a1", "full_b0", "full_b1", "full_b2", "empty_b0", "empty_b1", "empty_b2",
+                             "full_d0", "full_d1", "empty_d0", "empty_d1", "st_ready0", "st_ready1", "st_ready2", "st_done0", "st_done1", "st_done2"]
+                    print("status", w[0])
+                    for k in range(16):
+                        off, par, blk = w[4 + 3 * k : 7 + 3 * k]
+                        if off:
+                            print(f"  warp {k:2d}: waiting {names[(off - 219136) // 8] if 0 <= (off - 219136) // 8 < 20 else off} parity {par} block {blk}")
+        raise SystemExit(1)
