@@ -54,6 +54,7 @@ _SIGNATURES = {
     "gw_latent_edge_features": (ctypes.c_int, [_vp, _vp, _vp]),
     "gw_plan_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
     "gw_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
+    "gw_debug_trace_next": (ctypes.c_int, [_vp, _i32, _vp]),
     "gw_timing_enable": (ctypes.c_int, [_vp, _i32]),
     "gw_timing_num_tags": (_i32, []),
     "gw_timing_tag_name": (ctypes.c_char_p, [_i32]),
@@ -241,6 +242,13 @@ class Plan:
         arr = (_i32 * 64)()
         self.lib.gw_plan_debug(self.handle, arr)
         return list(arr)
+
+    def trace_next(self, tag_name: str):
+        """Arms the in-kernel event trace for the next chain of kernel class `tag_name`; returns the int64 buffer [8,1024,2]."""
+        names = [self.lib.gw_timing_tag_name(i).decode() for i in range(int(self.lib.gw_timing_num_tags()))]
+        buf = torch.zeros((8, 1024, 2), dtype=torch.int64, device=self.device)
+        _check(self.lib.gw_debug_trace_next(self.handle, names.index(tag_name), ctypes.c_void_p(buf.data_ptr())))
+        return buf
 
     def timing_enable(self, on: bool):
         _check(self.lib.gw_timing_enable(self.handle, 1 if on else 0))

@@ -125,6 +125,8 @@ struct gw_plan {
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
+  long long* trace_buf = nullptr;   // debug: device buffer [8][1024][2] handed to the next chain launched under trace_tag
+  int trace_tag = -1;
   int32_t* tc_status_host = nullptr;  // 16 words, pinned + mapped: stays readable by the host after a device trap
   int32_t* tc_status_dev = nullptr;
   TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node, tc_dec_out;
@@ -222,6 +224,10 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
 static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
   ch.status = p->tc_status_dev;
+  if (p->trace_buf && p->cur_tag == p->trace_tag) {
+    ch.trace = p->trace_buf;
+    p->trace_buf = nullptr;  // one launch only
+  }
   cudaError_t e;
   {
     TimedLaunch t(p, st);
@@ -1071,6 +1077,13 @@ int gw_plan_status(gw_plan* p, int32_t* status_out, void* stream) {
     return 1;
   }
   if (h[0]) h[0] = 0;
+  return 0;
+}
+
+int gw_debug_trace_next(gw_plan* p, int32_t tag, int64_t* device_buf) {
+  GW_CHECK(p != nullptr, "null plan");
+  p->trace_buf = (long long*)device_buf;
+  p->trace_tag = tag;
   return 0;
 }
 

@@ -80,6 +80,7 @@ struct TcChain {
   int32_t n_layers = 0;
   int32_t split = 1;          // 1: fp16 hi+lo operands, 3 MMAs per product (fp32-faithful); 0: bf16 single MMA
   int32_t* status = nullptr;  // device word: bit0 = operand exceeded the fp16 range, bit1 = pipeline timeout
+  long long* trace = nullptr; // optional debug timeline: [8 roles][1024 events][2] = {clock64, code}; CTA 0 only
   TcLayer layer[TC_MAX_LAYERS];
 };
 

@@ -126,6 +126,9 @@ int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
 /* Raw copy of the plan's 64-word host-mapped status block (no CUDA call: usable after a device fault):
  * word 0 = status flags; words 4+3w.. = {barrier byte offset, parity, block} of the wait warp w timed out on. */
 int gw_plan_debug(gw_plan* plan, int32_t* out64);
+/* Debug: the next tensor-core chain launched for kernel class `tag` writes a clock64 event timeline of its CTA 0 into
+ * device_buf ([8 roles][1024 events][2] int64, zero-initialised by the caller). */
+int gw_debug_trace_next(gw_plan* plan, int32_t tag, int64_t* device_buf);
 
 /* Per-launch device timing for bench.py's live roofline measurement.  When enabled, every kernel this library
  * launches for the plan is bracketed by a cudaEvent pair recorded on the launching stream and attributed to a kernel
