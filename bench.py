@@ -124,8 +124,21 @@ def time_cpu_reference(lat_lons, step_batch, sample_batch, steps, warmup):
     from oracle import restate
 
     cores = os.cpu_count()
-    torch.set_num_threads(cores)
     sd, g, x = oracle_inputs(lat_lons, sample_batch)
+    # give the CPU path its better thread count: all logical cores or one thread per physical core (probe: one Processor
+    # pass on one sample; the untimed warm-up forwards then run at the chosen setting)
+    best_n, best_t = cores, None
+    with torch.no_grad():
+        x1, ei1, ea1 = restate.encoder_forward(sd, g, x[:1])
+        for n in sorted({cores, max(1, cores // 2)}, reverse=True):
+            torch.set_num_threads(n)
+            t0 = time.perf_counter()
+            restate.processor_forward(sd, x1, ei1, ea1, 9)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_n, best_t = n, dt
+    torch.set_num_threads(best_n)
+    cores = best_n
     for _ in range(warmup):
         restate.forecaster_forward(sd, g, x)
     ts = []
@@ -203,12 +216,36 @@ def main():
             return y_all
         return y
 
+    # End-to-end step through the public module call: every step copies its inputs in from pinned host memory and its
+    # forecast back out.  The copies run on their own streams (double-buffered), so step i+1's input upload and step
+    # i-1's download overlap step i's compute -- the steady state of a real rollout / evaluation loop.
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    x_bufs = [torch.empty_like(x), torch.empty_like(x)]
+    out_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
+    e2e_state = {"i": 0, "used": [None, None]}
+
     def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        y = model(xd)
+        i = e2e_state["i"]
+        e2e_state["i"] = i + 1
+        cur = torch.cuda.current_stream(dev)
+        b = i & 1
+        if e2e_state["used"][b] is not None:
+            s_in.wait_event(e2e_state["used"][b])  # step i-2 has finished reading this input buffer
+        with torch.cuda.stream(s_in):
+            x_bufs[b].copy_(x_host, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+        cur.wait_event(ev_in)
+        y = model(x_bufs[b])
         if world > 1:
             all_gather_batch(y, world * a.batch)
-        out_host.copy_(y, non_blocking=True)
+        ev_c = torch.cuda.Event()
+        ev_c.record(cur)
+        e2e_state["used"][b] = ev_c
+        s_out.wait_event(ev_c)
+        with torch.cuda.stream(s_out):
+            out_bufs[b].copy_(y, non_blocking=True)
+        y.record_stream(s_out)
         return y
 
     def sync_all():
@@ -223,6 +260,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(s_in), cur.wait_stream(s_out)  # the timed region ends when the last download has landed
         e1.record()
         torch.cuda.synchronize(dev)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
