@@ -131,7 +131,8 @@ struct gw_plan {
   int32_t* tc_status_dev = nullptr;
   TcMlp tc_enc_node, tc_enc_edge, tc_enc_mnode, tc_dec_edge, tc_dec_node, tc_dec_out;
   bool tc_dec_out_ok = false;  // node_decoder fits the chain kernel (hidden_dec multiple of 64, 2 hidden layers)
-  DevBuf<float> agg_mesh;     // [chunk*n_mesh, De] encoder aggregation (segment sums)
+  DevBuf<float> agg_mesh;     // [max_batch*n_mesh, De] per-mesh-node aggregation (segment sums) of the encoder / processor blocks
+  DevBuf<float> agg_grid;     // [chunk*n_out, De] per-lat/lon-point aggregation of the decoder block
   std::vector<TcMlp> tc_proc_edge, tc_proc_node;
   // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
   bool timing = false;
@@ -664,8 +665,13 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
       {  // x' = LN(MLP([x ; sum_in e'])) + x
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
+        {  // per-node sum of incoming e' rows (contiguous CSR segments of <= 7 rows): coalesced reduction kernel, so the
+           // chain stages two plain row streams
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_segsum(e_next, De, De, g.ptr, nullptr, El, H, nb, p->agg_mesh.p, De, st));
+        }
         ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
-        ch.a0[1] = src_segsum(e_next, De, De, g.ptr, nullptr, El);
+        ch.a0[1] = src_stream(p->agg_mesh.p, De, De, H);
         ch.K0 = Dn + De;
         ch.layer[0] = tc_layer(p->tc_proc_node[k].w0, mn.b[0], true, true);
         ch.layer[1] = tc_layer(p->tc_proc_node[k].w1, mn.b[1], true, true);
@@ -759,7 +765,11 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
       {  // lat/lon node update (x == 0, so only the aggregate half of W1 and no residual)
         TcChain ch;
         ch.rows_per_sample = No, ch.batch = cb;
-        ch.a0[0] = src_segsum(eprime, De, De, p->dec_ptr.p, nullptr, Ed);
+        {
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_segsum(eprime, De, De, p->dec_ptr.p, nullptr, Ed, No, cb, p->agg_grid.p, De, st));
+        }
+        ch.a0[0] = src_stream(p->agg_grid.p, De, De, No);
         ch.K0 = De;
         ch.layer[0] = tc_layer(p->tc_dec_node.w0, mn.b[0], true, true);
         ch.layer[1] = tc_layer(p->tc_dec_node.w1, mn.b[1], true, true);
@@ -907,7 +917,8 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->xbuf0.alloc(B * d.n_mesh * Dn) | p->xbuf1.alloc(B * d.n_mesh * Dn);
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
-  rc |= p->agg_mesh.alloc(chunk * d.n_mesh * De);
+  rc |= p->agg_mesh.alloc(B * d.n_mesh * De);
+  if (d.precision != GW_PREC_FP32_SIMT) rc |= p->agg_grid.alloc(chunk * d.n_out * De);
   if (rc) {
     std::string keep = gw::g_err;
     gw_plan_destroy(p);
@@ -931,7 +942,7 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
-  p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release();
+  p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release(), p->agg_grid.release();
   if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
