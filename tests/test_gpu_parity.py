@@ -148,3 +148,21 @@ def test_full_size_properties_1deg(precision):
     err = float((y1.cpu() - ref).abs().max())
     print(f"1deg [{precision}] max|gpu - oracle| = {err:.3e}")
     assert err < TOL
+
+
+def test_bf16_precision_against_oracle():
+    """precision="bf16" (BASELINE configs 3/4): one bf16 tcgen05 MMA per product, fp32 accumulation.  Its own tolerance:
+    bf16 operands carry 8 significand bits, so through ~60 LayerNorm'd GEMM layers we accept 2e-2 max-abs (measured 2.7e-3) on O(1) outputs."""
+    from graph_weather_b200 import GraphWeatherForecaster
+    from oracle import restate, weights
+
+    ll = _grid(10)
+    sd = weights.make_state_dict(weights.forecaster_shapes(), 8)
+    x = weights.make_features(2, len(ll), 102, 8)
+    model = GraphWeatherForecaster(ll, precision="bf16").cuda()
+    model.load_state_dict(sd)
+    out = model(x.cuda()).cpu()
+    ref = restate.forecaster_forward(sd, restate.build_forecaster_graphs(ll), x)
+    err = float((out - ref).abs().max())
+    print(f"bf16 max|gpu - oracle| = {err:.3e}")
+    assert err < 2e-2
