@@ -49,9 +49,16 @@ constexpr int ST_STRIDE = 128;                  // staging row: 32 fp32; 16-byte
 constexpr int ST_BYTES = TILE_M * ST_STRIDE;    // one [128 rows x 32 cols] fp32 piece
 constexpr int NUM_MOVERS = 160;   // five warps; warp g owns staging buffer g (pieces p with p % 5 == g)
 constexpr int MOVER_GROUP = 32;
-constexpr int NUM_WORKERS = 256;  // thread (row, h): tile row = TMEM lane, h = which 32-column half of each 64-column chunk
+#ifndef GW_WSPLIT
+#define GW_WSPLIT 2
+#endif
+constexpr int WSPLIT = GW_WSPLIT;          // worker threads per tile row (2 or 4): each owns 64/WSPLIT columns of every 64-column chunk
+constexpr int WCOLS = 64 / WSPLIT;         // columns per worker thread per chunk (32 or 16)
+constexpr int NUM_WORKERS = 128 * WSPLIT;  // thread (row, hq): tile row = TMEM lane; 4 worker warps per scheduler hide each other's latencies
+constexpr int WORKER_WARPS = NUM_WORKERS / 32;
 constexpr int PAR_LAYERS = 6;     // per-layer parameter rows staged in shared memory (bias; LayerNorm gamma/beta for <= 2 layers)
-constexpr int NUM_THREADS = NUM_WORKERS + NUM_MOVERS + 64;  // workers 0-7, movers 8-12, weight producer 13, MMA issuer 14
+constexpr int NUM_THREADS = NUM_WORKERS + NUM_MOVERS + 64;  // workers first, then 5 mover warps, weight producer, MMA issuer
+constexpr int WARP_MOVER0 = WORKER_WARPS, WARP_PRODUCER = WORKER_WARPS + 5, WARP_MMA = WORKER_WARPS + 6;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
 constexpr int OFF_ST = OFF_B + B_STAGES * B_STAGE_BYTES;
@@ -155,7 +162,7 @@ struct Tracer {  // debug timeline of CTA 0 (one elected thread per role); a nul
     }
   }
 };
-__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory"); }
 
 // tcgen05.ld 32 lanes x 32 columns of 32-bit: thread t of the warp receives TMEM lane (lane_base+t), columns c..c+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -174,6 +181,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
@@ -266,14 +289,14 @@ __device__ __forceinline__ float4 src_load4(const RowSrc& s, int b, int i, int c
   }
 }
 
-// Split 32 fp32 values into fp16 hi/lo (or bf16) and store them as four 16-byte chunks per part into the swizzled
-// K-major operand tile: row r, logical 16B chunk j lives at chunk position j ^ (r & 7).
-__device__ __forceinline__ void store_operand_piece(uint8_t* slot, int r, int h, const float (&v)[32], bool split,
-                                                     float& amax) {
+// Split NV fp32 values (NV = 16 or 32) into fp16 hi/lo (or bf16) and store them as NV/8 16-byte chunks per part into the
+// swizzled K-major operand tile: row r, logical 16B chunk j (j0 .. j0+NV/8-1 of the row's 8) lives at chunk position j ^ (r & 7).
+template <int NV>
+__device__ __forceinline__ void store_operand_piece(uint8_t* slot, int r, int j0, const float (&v)[NV], bool split, float& amax) {
   uint8_t* row_hi = slot + r * 128;
   uint8_t* row_lo = row_hi + A_HALF_BYTES;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NV / 8; ++c) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -291,7 +314,7 @@ __device__ __forceinline__ void store_operand_piece(uint8_t* slot, int r, int h,
         lo[e] = 0;
       }
     }
-    const int chunk = ((h * 4 + c) ^ (r & 7)) * 16;
+    const int chunk = ((j0 + c) ^ (r & 7)) * 16;
     *reinterpret_cast<uint4*>(row_hi + chunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (split) *reinterpret_cast<uint4*>(row_lo + chunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
     for (int i = 0; i < ST_BUFS; ++i) mbar_init(bar_st_ready + 8 * i, MOVER_GROUP), mbar_init(bar_st_done + 8 * i, NUM_WORKERS);
     fence_barrier_init();
   }
-  if (warp == 14) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
+  if (warp == WARP_MMA) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
   // Warp ids are assigned by priority: the SM's warp arbiter favours the highest eligible warp id, so the roles that
   // others wait FOR (MMA issuer 14, weight producer 13, movers 8-12) sit above the workers (0-7), which spend much of
   // their time polling mbarriers.  (With the opposite order the pollers starve the very warps they are waiting on.)
-  if (warp == 13) {
+  if (warp == WARP_PRODUCER) {
     // ===================================== weight producer =====================================================
     if (lane == 0) {
       uint32_t bi = 0;
@@ -387,7 +410,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == WARP_MMA) {
     // ===================================== MMA issuer ==========================================================
     if (lane == 0) {
       uint32_t bi = 0, fi = 0, li = 0;
@@ -449,7 +472,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= WARP_MOVER0) {
     // ===================================== movers ==============================================================
     // Mover warp g owns staging buffer g and fills the pieces p with p % ST_BUFS == g, so ST_BUFS pieces are in flight.
     //  * aligned stream / broadcast / gather rows: 16-byte cp.async (LDGSTS) straight into staging, 8 lanes per 128-byte
@@ -458,7 +481,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
     // Staging rows are 128 B with the 16-byte chunks XOR-swizzled by (row & 7): conflict-free for the movers' 8-lanes-per-
     // row writes and for the workers' thread-per-row reads.  Output pieces are drained with coalesced 16-byte stores
     // when the buffer is recycled.
-    const int mgroup = warp - 8;
+    const int mgroup = warp - WARP_MOVER0;
     const int rsub = lane >> 3, ck = lane & 7;
     const uint32_t st_buf = sbase + OFF_ST + mgroup * ST_BYTES;
     const uint32_t bar_ready = bar_st_ready + 8 * mgroup, bar_done = bar_st_done + 8 * mgroup;
@@ -646,36 +669,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
     if (my_use > 0) retire();  // drain my last piece
   } else {
     // ===================================== workers: operand conversion + epilogues ============================
-    const int q = warp & 3;          // TMEM lane quadrant this warp may access
-    const int h = warp >> 2;         // which 32-column half of every 64-column chunk this thread owns
-    const int r = 32 * q + lane;     // tile row == TMEM lane
-    const int wtid = h * 128 + r;
-    const uint32_t st_row = sbase + OFF_ST + r * ST_STRIDE;  // + buffer * ST_BYTES + ((k ^ (r & 7)) << 4) for 16-byte chunk k
+    // Thread (q, lane, hq): tile row r = 32q + lane (= TMEM lane; a warp can only read the lane quadrant warp % 4, which
+    // is also its scheduler), columns [64 s + WCOLS*hq, +WCOLS) of every 64-column chunk s.  Staging pieces are the two
+    // 32-column halves of a chunk; thread hq reads its WCOLS columns of the half h = hq / (WSPLIT/2).
+    const int q = warp & 3;
+    const int hq = warp >> 2;                     // 0 .. WSPLIT-1
+    const int h = hq / (WSPLIT / 2);              // which 32-column staging half holds my columns
+    const int sub = hq % (WSPLIT / 2);            // which WCOLS-column part of that half
+    const int r = 32 * q + lane;                  // tile row == TMEM lane
+    const int wtid = hq * 128 + r;
     const int rsw = r & 7;
+    constexpr int NQ = WCOLS / 4;                 // 16-byte groups per thread per piece (8 or 4)
+    const int j0 = hq * (WCOLS / 8);              // my first logical 16-byte chunk in an operand row (8 chunks of 8 halfs)
+    const uint32_t st_row = sbase + OFF_ST + r * ST_STRIDE;  // + buffer * ST_BYTES + ((k ^ rsw) << 4) for 16-byte group k
     const uint32_t par_base = sbase + OFF_PAR, lnp_base = sbase + OFF_LNP;
     float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
     float* ln_y = ln_x + NUM_WORKERS;
     uint32_t fi = 0, li = 0, pn = 0;
     float amax = 0.f;
     Tracer tr;
-    tr.init(ch.trace, 5 + h, q == 0 && lane == 0);
+    tr.init(ch.trace, 5 + (hq & 1), q == 0 && lane == 0 && hq < 2);
 
     auto piece_wait = [&](uint32_t p) { mbar_wait(bar_st_ready + 8 * (p % ST_BUFS), (p / ST_BUFS) & 1, ch.status); };
     auto piece_done = [&](uint32_t p) { mbar_arrive(bar_st_done + 8 * (p % ST_BUFS)); };
-    // A staging buffer serves pieces of either half-group in turn.  The half that does not own piece p still waits for
-    // its ready phase and arrives on its done barrier ("observes" it), so that every worker sees every phase of every
-    // barrier in order and a buffer is never refilled while some warp has yet to pass the previous phase (a parity
-    // wait would otherwise be ambiguous by two phases).  take(): my piece -> read (accumulating or not) and release;
-    // the other half's piece -> observe.
-    auto take = [&](uint32_t p, bool mine, float (&v)[32], bool accumulate) {
+    // A staging buffer serves pieces of either column half in turn.  Threads whose columns are in the other half still
+    // wait for the piece's ready phase and arrive on its done barrier ("observe" it), so that every worker sees every
+    // phase of every barrier in order and a buffer is never refilled while some warp has yet to pass the previous phase
+    // (a parity wait would otherwise be ambiguous by two phases).  take(): my half -> read my WCOLS floats and release.
+    auto take = [&](uint32_t p, bool mine, float (&v)[WCOLS], bool accumulate) {
       tr.ev(10000 + (int)p);
       piece_wait(p);
       tr.ev(20000 + (int)p);
       if (mine) {
         const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 t = lds128(a + ((k ^ rsw) << 4));
+        for (int k = 0; k < NQ; ++k) {
+          const float4 t = lds128(a + (((sub * NQ + k) ^ rsw) << 4));
           if (accumulate) {
             v[4 * k] += t.x, v[4 * k + 1] += t.y, v[4 * k + 2] += t.z, v[4 * k + 3] += t.w;
           } else {
@@ -685,15 +714,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
       }
       piece_done(p);
     };
-    auto piece_write = [&](uint32_t p, const float (&v)[32]) {
+    auto piece_write = [&](uint32_t p, const float (&v)[WCOLS]) {
       const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sts128(a + ((k ^ rsw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+      for (int k = 0; k < NQ; ++k)
+        sts128(a + (((sub * NQ + k) ^ rsw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
     };
-    // v = acc * wscale_inv + bias for 32 columns (bias row lives in shared memory, zero past n_valid)
-    auto scale_bias = [&](float (&v)[32], float wsi, uint32_t bias_s) {
+    // v = acc * wscale_inv + bias for my WCOLS columns (bias row lives in shared memory, zero past n_valid)
+    auto scale_bias = [&](float (&v)[WCOLS], float wsi, uint32_t bias_s) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < NQ; ++k) {
         const float4 b4 = lds128(bias_s + 16 * k);
         v[4 * k] = fmaf(v[4 * k], wsi, b4.x), v[4 * k + 1] = fmaf(v[4 * k + 1], wsi, b4.y);
         v[4 * k + 2] = fmaf(v[4 * k + 2], wsi, b4.z), v[4 * k + 3] = fmaf(v[4 * k + 3], wsi, b4.w);
@@ -709,20 +739,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
           const int colc = 64 * c;
           const RowSrc& src = (colc < w0) ? ch.a0[0] : ch.a0[1];
           const bool two = (colc < w0 || ch.a0[1].kind != SRC_NONE) && src.kind == SRC_GATHER_BCAST_RELU;
-          float v[32];
+          float v[WCOLS];
           take(pn + 0, h == 0, v, false);
           take(pn + 1, h == 1, v, false);
           if (two) {
             take(pn + 2, h == 0, v, true);
             take(pn + 3, h == 1, v, true);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < WCOLS; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           pn += two ? 4 : 2;
           tr.ev(500 + c);
           mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
           tr.ev(510 + c);
-          store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
+          store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
           fence_proxy_async();
           mbar_arrive(bar_full_a + 8 * slot);
           tr.ev(520 + c);
@@ -751,68 +781,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
         float mean = 0.f, rstd = 1.f;
         if (has_ln) {
-          // LayerNorm statistics of this row (shared by the two threads h = 0, 1): mean, then centred second moment,
-          // like torch's CPU kernel, both straight from TMEM (cheaper than holding 128 values in registers).
+          // LayerNorm statistics of this row (shared by the WSPLIT threads of the row): mean, then centred second moment,
+          // like torch's CPU kernel, both straight from TMEM (cheaper than holding the row in registers).
           float s1 = 0.f;
           for (int s = 0; s < np; ++s) {
-            const int c0 = 64 * s + 32 * h;
+            const int c0 = 64 * s + WCOLS * hq;
             if (c0 >= N) break;
-            float v[32];
-            tmem_ld32(taddr + c0, v);
+            float v[WCOLS];
+            tmem_ldw(taddr + c0, v);
             scale_bias(v, wsi, bias_s + 4 * c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s1 += v[j];
+            for (int j = 0; j < WCOLS; ++j) s1 += v[j];
           }
           ln_x[wtid] = s1;
           named_bar_workers();
-          mean = (s1 + ln_x[wtid ^ 128]) / (float)nval;
+          float tot = 0.f;
+#pragma unroll
+          for (int t = 0; t < WSPLIT; ++t) tot += ln_x[t * 128 + r];  // same order for every thread of the row
+          mean = tot / (float)nval;
           float s2 = 0.f;
           for (int s = 0; s < np; ++s) {
-            const int c0 = 64 * s + 32 * h;
+            const int c0 = 64 * s + WCOLS * hq;
             if (c0 >= N) break;
-            float v[32];
-            tmem_ld32(taddr + c0, v);
+            float v[WCOLS];
+            tmem_ldw(taddr + c0, v);
             scale_bias(v, wsi, bias_s + 4 * c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < WCOLS; ++j) {
               const float x = v[j] - mean;
               s2 = fmaf(x, x, s2);
             }
           }
           ln_y[wtid] = s2;
           named_bar_workers();
-          rstd = 1.0f / sqrtf((s2 + ln_y[wtid ^ 128]) / (float)nval + 1e-5f);
+          float tot2 = 0.f;
+#pragma unroll
+          for (int t = 0; t < WSPLIT; ++t) tot2 += ln_y[t * 128 + r];
+          rstd = 1.0f / sqrtf(tot2 / (float)nval + 1e-5f);
         }
         for (int s = 0; s < np; ++s) {
-          const int c0 = 64 * s + 32 * h;
-          const bool have = c0 < N;                    // my half of this chunk exists
-          const bool have1 = 64 * s + 32 < N;          // the h = 1 half exists
-          float v[32];
+          const int c0 = 64 * s + WCOLS * hq;
+          const bool have = c0 < N;                    // my columns of this chunk exist
+          const bool have1 = 64 * s + 32 < N;          // the second 32-column half of this chunk exists
+          float v[WCOLS];
           if (have) {
-            tmem_ld32(taddr + c0, v);
+            tmem_ldw(taddr + c0, v);
             scale_bias(v, wsi, bias_s + 4 * c0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int j = 0; j < WCOLS; ++j) v[j] = 0.f;
           }
           // staged pieces of this chunk in the movers' order: add0(h0,h1), add1(h0,h1), residual/out(h0,h1)
           if (has_add0) {
-            take(pn++, h == 0, v, true);
-            if (have1) take(pn++, h == 1, v, true);
+            take(pn++, h == 0 && have, v, true);
+            if (have1) take(pn++, h == 1 && have, v, true);
           }
           if (has_add1) {
-            take(pn++, h == 0, v, true);
-            if (have1) take(pn++, h == 1, v, true);
+            take(pn++, h == 0 && have, v, true);
+            if (have1) take(pn++, h == 1 && have, v, true);
           }
           if (have) {
             if (relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int j = 0; j < WCOLS; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (has_ln) {
               const float nm = -mean * rstd;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
+              for (int k = 0; k < NQ; ++k) {
                 const float4 g4 = lds128(g_s + 4 * c0 + 16 * k), e4 = lds128(b_s + 4 * c0 + 16 * k);
                 v[4 * k] = fmaf(fmaf(v[4 * k], rstd, nm), g4.x, e4.x);
                 v[4 * k + 1] = fmaf(fmaf(v[4 * k + 1], rstd, nm), g4.y, e4.y);
@@ -822,19 +858,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             }
             if (nval < N) {  // padded output columns (e.g. 78 of 80) must stay exactly zero
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < WCOLS; ++j)
                 if (c0 + j >= nval) v[j] = 0.f;
             }
           }
           if (has_ro) {
             for (int hh = 0; hh < (have1 ? 2 : 1); ++hh, ++pn) {
               piece_wait(pn);
-              if (hh == h) {
+              if (hh == h && have) {
                 if (has_res) {
                   const uint32_t a = st_row + (pn % ST_BUFS) * ST_BYTES;
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const float4 t = lds128(a + ((k ^ rsw) << 4));
+                  for (int k = 0; k < NQ; ++k) {
+                    const float4 t = lds128(a + (((sub * NQ + k) ^ rsw) << 4));
                     v[4 * k] += t.x, v[4 * k + 1] += t.y, v[4 * k + 2] += t.z, v[4 * k + 3] += t.w;
                   }
                 }
@@ -844,11 +880,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             }
           }
           tr.ev(700 + 10 * l + s);
-          if (feeds) {  // publish this 64-column chunk of the next operand as soon as both halves are written
+          if (feeds) {  // publish this 64-column chunk of the next operand once all WSPLIT column parts are written
             const uint32_t f = fi + s, slot = f % A_SLOTS, n = f / A_SLOTS;
             mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
             tr.ev(800 + 10 * l + s);
-            store_operand_piece(smem + OFF_A + slot * A_SLOT_BYTES, r, h, v, split, amax);
+            store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
             fence_proxy_async();
             mbar_arrive(bar_full_a + 8 * slot);
           }
@@ -864,7 +900,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 14) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
