@@ -8,6 +8,8 @@ from .models import (  # noqa: F401
     AssimilatorEncoder,
     Decoder,
     Encoder,
+    GraphCast,
+    GraphCastConfig,
     GraphWeatherAssimilator,
     GraphWeatherAssimilatorConfig,
     GraphWeatherForecaster,
@@ -17,5 +19,5 @@ from .models import (  # noqa: F401
 
 __all__ = [
     "GraphWeatherForecaster", "GraphWeatherForecasterConfig", "GraphWeatherAssimilator", "GraphWeatherAssimilatorConfig",
-    "Encoder", "Processor", "Decoder", "AssimilatorEncoder", "AssimilatorDecoder",
+    "GraphCast", "GraphCastConfig", "Encoder", "Processor", "Decoder", "AssimilatorEncoder", "AssimilatorDecoder",
 ]  # fmt: skip

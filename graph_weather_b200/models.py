@@ -636,3 +636,106 @@ class GraphWeatherAssimilator(nn.Module, PyTorchModelHubMixin):
         plan.forward(f, out)
         _maybe_check(plan)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GraphCast wrapper (graphcast/model.py)
+# ---------------------------------------------------------------------------------------------------------------
+class GraphCast(nn.Module):
+    """graph_weather/models/graphcast/model.py:21-285: Encoder + Processor + Decoder with hierarchical gradient-checkpoint
+    controls and `efficient_batching`.  Forward-only here: the checkpoint setters are accepted and recorded (they do not
+    change forward results in the reference either), and efficient / replicated batching are the same computation -- the
+    CUDA path always shares one graph across the batch (the reference proves the equivalence in
+    tests/models/layers/test_efficient_batching.py)."""
+
+    def __init__(self, lat_lons: list, resolution: int = 2, input_dim: int = 78, output_dim: int = 78, hidden_dim: int = 256,
+                 num_processor_blocks: int = 9, hidden_layers: int = 2, mlp_norm_type: str = "LayerNorm",
+                 use_checkpointing: bool = False, efficient_batching: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+        super().__init__()
+        lat_lons = _latlon_list(lat_lons)
+        self.lat_lons = lat_lons
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.efficient_batching = efficient_batching
+        self.encoder = Encoder(lat_lons=lat_lons, resolution=resolution, input_dim=input_dim, output_dim=hidden_dim,
+                               output_edge_dim=hidden_dim, hidden_dim_processor_node=hidden_dim, hidden_dim_processor_edge=hidden_dim,
+                               hidden_layers_processor_node=hidden_layers, hidden_layers_processor_edge=hidden_layers,
+                               mlp_norm_type=mlp_norm_type, use_checkpointing=use_checkpointing,
+                               efficient_batching=efficient_batching, precision=precision)  # fmt: skip
+        self.processor = Processor(input_dim=hidden_dim, edge_dim=hidden_dim, num_blocks=num_processor_blocks,
+                                   hidden_dim_processor_node=hidden_dim, hidden_dim_processor_edge=hidden_dim,
+                                   hidden_layers_processor_node=hidden_layers, hidden_layers_processor_edge=hidden_layers,
+                                   mlp_norm_type=mlp_norm_type, use_checkpointing=use_checkpointing, precision=precision)  # fmt: skip
+        self.decoder = Decoder(lat_lons=lat_lons, resolution=resolution, input_dim=hidden_dim, output_dim=output_dim,
+                               hidden_dim_processor_node=hidden_dim, hidden_dim_processor_edge=hidden_dim,
+                               hidden_layers_processor_node=hidden_layers, hidden_layers_processor_edge=hidden_layers,
+                               mlp_norm_type=mlp_norm_type, hidden_dim_decoder=hidden_dim, hidden_layers_decoder=hidden_layers,
+                               use_checkpointing=use_checkpointing, efficient_batching=efficient_batching, precision=precision)  # fmt: skip
+        self._checkpoint_model = False
+        self._checkpoint_encoder = False
+        self._checkpoint_processor_segments = 0
+        self._checkpoint_decoder = False
+        dims = dict(self.encoder._dims)
+        dims.update(n_out=self.decoder.num_latlons, n_dec_edges=self.decoder._dims["n_dec_edges"], out_dim=output_dim,
+                    residual_dim=output_dim, hidden_dec=hidden_dim, hidden_layers_dec=hidden_layers, num_blocks=num_processor_blocks)  # fmt: skip
+        self._engine = _Engine(dims, precision)
+        self._engine.graph_uploaders += [self.encoder._upload_graphs, self.decoder._upload_graphs]
+
+    # hierarchical checkpointing controls (model.py:118-174)
+    def set_checkpoint_model(self, checkpoint_flag: bool):
+        self._checkpoint_model = checkpoint_flag
+        if checkpoint_flag:
+            self._checkpoint_encoder = False
+            self._checkpoint_processor_segments = 0
+            self._checkpoint_decoder = False
+
+    def set_checkpoint_encoder(self, checkpoint_flag: bool):
+        self._checkpoint_encoder = checkpoint_flag
+
+    def set_checkpoint_processor(self, checkpoint_segments: int):
+        self._checkpoint_processor_segments = checkpoint_segments
+
+    def set_checkpoint_decoder(self, checkpoint_flag: bool):
+        self._checkpoint_decoder = checkpoint_flag
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        if features.device.type != "cuda":
+            _no_host_path("GraphCast.forward")
+        if features.shape[-1] != self.output_dim:  # the reference adds the full input as the residual (model.py:203, decoder.py:93)
+            raise RuntimeError(f"The size of tensor a ({self.output_dim}) must match the size of tensor b ({features.shape[-1]}) "
+                               "at non-singleton dimension 2")  # fmt: skip
+        B = features.shape[0]
+        plan = self._engine.ensure(features.device, B, [(k, v) for k, v in self.state_dict(keep_vars=True).items()])
+        f = features.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, self.decoder.num_latlons, self.output_dim), dtype=torch.float32, device=f.device)
+        plan.forward(f, out)
+        _maybe_check(plan)
+        return out
+
+
+class GraphCastConfig:
+    """graphcast/model.py:288-345: pre-defined checkpointing strategies."""
+
+    @staticmethod
+    def no_checkpointing(model: GraphCast):
+        model.set_checkpoint_model(False), model.set_checkpoint_encoder(False)
+        model.set_checkpoint_processor(0), model.set_checkpoint_decoder(False)
+
+    @staticmethod
+    def full_checkpointing(model: GraphCast):
+        model.set_checkpoint_model(True)
+
+    @staticmethod
+    def balanced_checkpointing(model: GraphCast):
+        model.set_checkpoint_model(False), model.set_checkpoint_encoder(True)
+        model.set_checkpoint_processor(-1), model.set_checkpoint_decoder(True)
+
+    @staticmethod
+    def processor_only_checkpointing(model: GraphCast):
+        model.set_checkpoint_model(False), model.set_checkpoint_encoder(False)
+        model.set_checkpoint_processor(-1), model.set_checkpoint_decoder(False)
+
+    @staticmethod
+    def fine_grained_checkpointing(model: GraphCast):
+        model.set_checkpoint_model(False), model.set_checkpoint_encoder(False)
+        model.set_checkpoint_processor(0), model.set_checkpoint_decoder(False)

@@ -125,6 +125,11 @@ def load_reference():
     models.AssimilatorEncoder, models.AssimilatorDecoder = aenc.AssimilatorEncoder, adec.AssimilatorDecoder
     fc = importlib.import_module("graph_weather.models.forecast")
     an = importlib.import_module("graph_weather.models.analysis")
+    if "graph_weather.models.graphcast" not in sys.modules:
+        gcp = types.ModuleType("graph_weather.models.graphcast")
+        gcp.__path__ = [os.path.join(base, "models", "graphcast")]
+        sys.modules["graph_weather.models.graphcast"] = gcp
+    gc = importlib.import_module("graph_weather.models.graphcast.model")
     ns = types.SimpleNamespace(
         MLP=gnb.MLP,
         GraphProcessor=gnb.GraphProcessor,
@@ -135,6 +140,8 @@ def load_reference():
         AssimilatorDecoder=adec.AssimilatorDecoder,
         GraphWeatherForecaster=fc.GraphWeatherForecaster,
         GraphWeatherAssimilator=an.GraphWeatherAssimilator,
+        GraphCast=gc.GraphCast,
+        GraphCastConfig=gc.GraphCastConfig,
     )
     _loaded = ns
     return ns

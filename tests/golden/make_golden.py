@@ -96,9 +96,29 @@ def run_assimilator(R, name="assimilator_readme"):
     print(name, "out", tuple(out.shape), "mean|out|", float(out.abs().mean()))
 
 
+def run_graphcast(R, name="graphcast_10deg_b2"):
+    """graphcast/model.py GraphCast, replicated and efficient batching (the reference's own equivalence pair)."""
+    lat_lons = grid(10)
+    shapes = weights.forecaster_shapes(feature_dim=78, aux_dim=0, hidden_dim_decoder=256)
+    sd = weights.make_state_dict(shapes, 5)
+    x = weights.make_features(2, len(lat_lons), 78, 5)
+    outs = {}
+    for eff in (False, True):
+        model = R.GraphCast(lat_lons, efficient_batching=eff).eval()
+        assert list(model.state_dict().keys()) == list(shapes.keys())
+        model.load_state_dict(sd)
+        R.GraphCastConfig.balanced_checkpointing(model)
+        with torch.no_grad():
+            outs[eff] = model(x)
+    print(name, "replicated vs efficient max diff", float((outs[False] - outs[True]).abs().max()))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), config=json.dumps(dict(step=10, batch=2, seed=5)),
+                        out=outs[False].numpy(), out_efficient=outs[True].numpy())  # fmt: skip
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     R = ref_shims.load_reference()
     for n, s in CASES.items():
         run_forecaster(R, n, s)
     run_assimilator(R)
+    run_graphcast(R)

@@ -69,3 +69,17 @@ def test_same_seed_same_init_as_reference():
     ref = R.GraphWeatherForecaster(ll).state_dict()
     assert list(mine.keys()) == list(ref.keys())
     assert all(torch.equal(mine[k], ref[k]) for k in ref)
+
+
+def test_graphcast_wrapper_contract():
+    from graph_weather_b200 import GraphCast, GraphCastConfig
+    from oracle import weights
+
+    ll = [(float(a), float(b)) for a in range(-90, 90, 30) for b in range(0, 360, 30)]
+    m = GraphCast(ll, efficient_batching=True)
+    shapes = weights.forecaster_shapes(feature_dim=78, aux_dim=0, hidden_dim_decoder=256)
+    assert list(m.state_dict().keys()) == list(shapes.keys())
+    GraphCastConfig.balanced_checkpointing(m)
+    assert (m._checkpoint_encoder, m._checkpoint_processor_segments, m._checkpoint_decoder) == (True, -1, True)
+    GraphCastConfig.full_checkpointing(m)
+    assert m._checkpoint_model and not m._checkpoint_encoder

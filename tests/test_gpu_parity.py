@@ -166,3 +166,23 @@ def test_bf16_precision_against_oracle():
     err = float((out - ref).abs().max())
     print(f"bf16 max|gpu - oracle| = {err:.3e}")
     assert err < 2e-2
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("efficient", [False, True])
+def test_graphcast_wrapper_matches_reference_fixture(golden_dir, precision, efficient):
+    """GraphCast (graphcast/model.py:21-285) with every checkpointing strategy: forward results do not depend on them."""
+    from graph_weather_b200 import GraphCast, GraphCastConfig
+    from oracle import weights
+
+    z = np.load(os.path.join(golden_dir, "graphcast_10deg_b2.npz"))
+    cfg = json.loads(str(z["config"]))
+    ll = _grid(cfg["step"])
+    model = GraphCast(ll, efficient_batching=efficient, precision=precision).cuda()
+    model.load_state_dict(weights.make_state_dict(weights.forecaster_shapes(feature_dim=78, aux_dim=0, hidden_dim_decoder=256), cfg["seed"]))
+    x = weights.make_features(cfg["batch"], len(ll), 78, cfg["seed"]).cuda()
+    ref = z["out_efficient" if efficient else "out"]
+    for strategy in (GraphCastConfig.no_checkpointing, GraphCastConfig.balanced_checkpointing, GraphCastConfig.full_checkpointing):
+        strategy(model)
+        out = model(x).cpu().numpy()
+        assert np.abs(out - ref).max() < TOL

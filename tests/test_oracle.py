@@ -45,3 +45,16 @@ def test_assimilator_restatement_matches_reference(golden_dir):
     x = weights.make_features(1, obs.shape[0], 2, cfg["seed"])
     out = restate.assimilator_forward(sd, g, x, obs)
     assert np.abs(out.numpy() - z["out"]).max() < 1e-5
+
+
+def test_graphcast_restatement_matches_reference(golden_dir):
+    """graphcast/model.py wrapper: Decoder with hidden 256 and the full input as residual; replicated == efficient batching."""
+    z = np.load(os.path.join(golden_dir, "graphcast_10deg_b2.npz"))
+    cfg = json.loads(str(z["config"]))
+    ll = _grid(cfg["step"])
+    g = restate.build_forecaster_graphs(ll)
+    sd = weights.make_state_dict(weights.forecaster_shapes(feature_dim=78, aux_dim=0, hidden_dim_decoder=256), cfg["seed"])
+    x = weights.make_features(cfg["batch"], len(ll), 78, cfg["seed"])
+    out = restate.forecaster_forward(sd, g, x, feature_dim=78)
+    assert np.abs(out.numpy() - z["out"]).max() < 1e-5
+    assert np.abs(z["out"] - z["out_efficient"]).max() < 1e-4  # the reference's own tolerance, test_efficient_batching.py:145
