@@ -11,7 +11,8 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgwb200.so")
+# GW_B200_LIB: diagnostics builds of the same library (tools/ablate.py); never a different implementation
+LIB_PATH = os.environ.get("GW_B200_LIB") or os.path.join(_HERE, "libgwb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gw_b200.h")
 
 PREC_FP32_SIMT, PREC_FP32_TC, PREC_BF16_TC = 0, 1, 2

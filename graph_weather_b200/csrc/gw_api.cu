@@ -225,6 +225,12 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
 static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
   ch.status = p->tc_status_dev;
+#ifdef GW_ABLATE
+  {
+    const char* abl = getenv("GW_ABLATE");  // re-read per launch: tools/ablate.py sweeps masks in one process
+    ch.ablate = abl ? atoi(abl) : 0;
+  }
+#endif
   if (p->trace_buf && p->cur_tag == p->trace_tag) {
     ch.trace = p->trace_buf;
     p->trace_buf = nullptr;  // one launch only
@@ -232,7 +238,8 @@ static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   cudaError_t e;
   {
     TimedLaunch t(p, st);
-    e = launch_chain_tc(ch, st);
+    static const int gen = getenv("GW_TC_KERNEL") ? atoi(getenv("GW_TC_KERNEL")) : 2;
+    e = gen == 2 ? launch_chain_tc(ch, st) : launch_chain_tc3(ch, st);
   }
   if (e != cudaSuccess) {
     set_error(std::string("tensor-core chain launch failed: ") + cudaGetErrorString(e));

@@ -18,7 +18,8 @@ cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* p
                           int rows, int batch, float* out, int ldo, cudaStream_t stream);
 
 // tcgen05 chain kernel (gw_tc.cu)
-cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream);
+cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream);   // gw_tc.cu: mover/staging generation (GW_TC_KERNEL=2)
+cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream);  // gw_tc3.cu: direct fragment-layout generation (default)
 // Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with
 // cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts).
 size_t tc_packed_bytes(int K_src, int N_src, int parts);

@@ -37,8 +37,18 @@
 
 #include "gw_internal.h"
 #include "gw_ops.h"
+#include "gw_tc_ptx.cuh"
 
 namespace gw {
+
+// Timing-attribution build (-DGW_ABLATE, tools/ablate.py): parts of the pipeline can be skipped at run time.  Results are
+// WRONG under any non-zero mask; the product build compiles every ABL() to false.
+#ifdef GW_ABLATE
+#define ABL(bit) ((ch.ablate & (bit)) != 0)
+#else
+#define ABL(bit) false
+#endif
+enum { ABL_FENCE = 1, ABL_TAKE = 2, ABL_CONVERT = 4, ABL_MOVE = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
 
 constexpr int TILE_M = 128;
 constexpr int A_SLOTS = 2, B_STAGES = 2, ST_BUFS = 5;
@@ -73,147 +83,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory li
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
 static_assert(OFF_ST % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
-// ------------------------------------------------------------------------------------------------------------------
-// PTX wrappers (syntax checked against cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp)
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU.  After ~4 s the thread records which barrier it was waiting on in the
-// (host-mapped) status block -- word 0 bit 1, words 1..5 = barrier byte offset, parity, thread, block, role tag -- and traps.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int32_t* status) {
-  if (status) {
-    extern __shared__ __align__(1024) uint8_t smem_dbg[];
-    atomicOr(status, 2);
-    const int w = threadIdx.x >> 5;  // one record per warp: {barrier byte offset in smem, parity, block}
-    status[4 + 3 * w + 0] = (int32_t)(bar - (uint32_t)__cvta_generic_to_shared(smem_dbg));
-    status[4 + 3 * w + 1] = (int32_t)parity;
-    status[4 + 3 * w + 2] = (int32_t)blockIdx.x;
-  }
-  __threadfence_system();
-  // give the other warps of this CTA time to record their own stuck waits before the context dies
-  for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity, status);
-  }
-}
-// Same, for threads that expect to wait long (movers): sleep between polls so they do not steal issue slots
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int32_t* status) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(200);
-    if (clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity, status);
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-struct Tracer {  // debug timeline of CTA 0 (one elected thread per role); a null buffer disables it
-  long long* p;
-  int n;
-  __device__ __forceinline__ void init(long long* base, int role, bool on) { p = (base && on && blockIdx.x == 0) ? base + role * 2048 : nullptr, n = 0; }
-  __device__ __forceinline__ void ev(int code) {
-    if (p && n < 1024) {
-      p[2 * n] = clock64();
-      p[2 * n + 1] = code;
-      ++n;
-    }
-  }
-};
 __device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory"); }
-
-// tcgen05.ld 32 lanes x 32 columns of 32-bit: thread t of the warp receives TMEM lane (lane_base+t), columns c..c+31
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
-__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format [7,10)/[10,13) (0 = F16, 1 = BF16), K-major A and B,
-// N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int N, int bf16) {
-  uint32_t f = bf16 ? 1u : 0u;
-  return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // movers: global rows <-> padded fp32 staging pieces
@@ -402,6 +272,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             for (int part = 0; part < parts; ++part, ++bi) {
               const uint32_t stage = bi % B_STAGES, n = bi / B_STAGES;
               mbar_wait(bar_empty_b + 8 * stage, (n & 1) ^ 1, ch.status);
+              if (ABL(ABL_WEIGHTS)) {
+                mbar_arrive(bar_full_b + 8 * stage);
+                continue;
+              }
               mbar_expect_tx(bar_full_b + 8 * stage, panel);
               bulk_g2s(sbase + OFF_B + stage * B_STAGE_BYTES, w + (size_t)(kc * parts + part) * panel, panel,
                        bar_full_b + 8 * stage);
@@ -443,8 +317,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
               const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, (kc | ks) != 0);
-              if (split) {
+                if (!ABL(ABL_MMA)) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, (kc | ks) != 0);
+              if (split && !ABL(ABL_MMA)) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_lo + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
               }
@@ -457,7 +331,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
               tc_fence_after();
               const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
+              for (int ks = 0; ks < 4; ++ks)
+                if (!ABL(ABL_MMA)) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
               tc_commit(bar_empty_b + 8 * stage);
               ++bi;
             }
@@ -495,7 +370,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
 
     auto retire = [&]() {  // wait until the workers are done with my previous piece, then store its output rows
       mbar_wait(bar_done, (my_use - 1) & 1, ch.status);
-      if (prev.out) {
+      if (prev.out && !ABL(ABL_MOVE)) {
         const int col = prev.c0 + 4 * ck;
         const bool vec = vec4_ok(prev.out, prev.ldo, col) && col + 4 <= prev.out_cols;
         if (col < prev.out_cols) {
@@ -528,7 +403,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
       prev = rt;
       ++my_use;
       const int kind = s0.kind;
-      if (kind == SRC_NONE) {
+      if (kind == SRC_NONE || ABL(ABL_MOVE)) {
         mbar_arrive(bar_ready);
         return;
       }
@@ -700,7 +575,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
       tr.ev(10000 + (int)p);
       piece_wait(p);
       tr.ev(20000 + (int)p);
-      if (mine) {
+      if (mine && !ABL(ABL_TAKE)) {
         const uint32_t a = st_row + (p % ST_BUFS) * ST_BYTES;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
@@ -752,8 +627,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
           tr.ev(500 + c);
           mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
           tr.ev(510 + c);
-          store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
-          fence_proxy_async();
+          if (!ABL(ABL_CONVERT)) store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
+          if (!ABL(ABL_FENCE)) fence_proxy_async();
           mbar_arrive(bar_full_a + 8 * slot);
           tr.ev(520 + c);
         }
@@ -780,7 +655,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
         tr.ev(610 + l);
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
         float mean = 0.f, rstd = 1.f;
-        if (has_ln) {
+        if (has_ln && !ABL(ABL_LN)) {
           // LayerNorm statistics of this row (shared by the WSPLIT threads of the row): mean, then centred second moment,
           // like torch's CPU kernel, both straight from TMEM (cheaper than holding the row in registers).
           float s1 = 0.f;
@@ -824,7 +699,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
           const bool have = c0 < N;                    // my columns of this chunk exist
           const bool have1 = 64 * s + 32 < N;          // the second 32-column half of this chunk exists
           float v[WCOLS];
-          if (have) {
+          if (have && !ABL(ABL_TMEM)) {
             tmem_ldw(taddr + c0, v);
             scale_bias(v, wsi, bias_s + 4 * c0);
           } else {
@@ -866,7 +741,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             for (int hh = 0; hh < (have1 ? 2 : 1); ++hh, ++pn) {
               piece_wait(pn);
               if (hh == h && have) {
-                if (has_res) {
+                if (has_res && !ABL(ABL_TAKE)) {
                   const uint32_t a = st_row + (pn % ST_BUFS) * ST_BYTES;
 #pragma unroll
                   for (int k = 0; k < NQ; ++k) {
@@ -874,7 +749,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
                     v[4 * k] += t.x, v[4 * k + 1] += t.y, v[4 * k + 2] += t.z, v[4 * k + 3] += t.w;
                   }
                 }
-                if (has_out) piece_write(pn, v);  // in place: each thread overwrites exactly the bytes it read
+                if (has_out && !ABL(ABL_TAKE)) piece_write(pn, v);  // in place: each thread overwrites exactly the bytes it read
               }
               piece_done(pn);
             }
@@ -884,8 +759,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc_kernel(const __gri
             const uint32_t f = fi + s, slot = f % A_SLOTS, n = f / A_SLOTS;
             mbar_wait(bar_empty_a + 8 * slot, (n & 1) ^ 1, ch.status);
             tr.ev(800 + 10 * l + s);
-            store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
-            fence_proxy_async();
+            if (!ABL(ABL_CONVERT)) store_operand_piece<WCOLS>(smem + OFF_A + slot * A_SLOT_BYTES, r, j0, v, split, amax);
+            if (!ABL(ABL_FENCE)) fence_proxy_async();
             mbar_arrive(bar_full_a + 8 * slot);
           }
         }

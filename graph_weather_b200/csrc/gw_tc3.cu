@@ -1,0 +1,691 @@
+// gw_tc3.cu -- the fused MLP-chain kernel on Blackwell tensor cores (tcgen05 + TMEM), precision GW_PREC_FP32_TC / BF16_TC.
+//
+// One persistent CTA per SM walks 128-row tiles of a gw::TcChain.  For every tile the whole chain
+//     A0 = assemble(row sources)                                   (stream / gather / relu(gather+const) ...)
+//     for each layer:  D = A . W^T  (tcgen05.mma, fp32 accumulate in TMEM)
+//                      v = D*s + bias + gathered addends ; ReLU | LayerNorm ; + residual
+//                      v -> global (fp32)  and/or  v -> split fp16 hi/lo -> shared memory = A operand of the next layer
+// runs without the activations ever leaving the SM: the reference's x[row]/x[col] gathers, cat, 3 Linear + LayerNorm and
+// residual (graph_net_block.py:131-135, 184-191) are one kernel per edge pass and one per node pass.
+//
+// fp32 fidelity on fp16 tensor cores: every fp32 operand a is split a = hi + lo (two fp16, 22 significand bits) and each
+// product is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.  Weights are pre-scaled by a power of two so their lo
+// parts stay normal; the scale is undone exactly in the epilogue.
+//
+// Layout of the work (this is the third generation; gw_tc.cu's mover/staging design spent 40 % of its time in mbarrier
+// hand-offs, measured with tools/ablate.py):
+//   * 16 worker warps, four per TMEM lane quadrant.  A worker reads the accumulator with tcgen05.ld.16x256b, whose register
+//     fragment gives four adjacent lanes eight consecutive columns of one row (32 B = one sector).  In that fragment layout
+//     the workers load gathered addends / residual rows and store outputs DIRECTLY from/to global memory with 8-byte
+//     accesses (8 rows x 32 B per warp instruction, every fetched sector fully used): no staging buffers, no mover warps,
+//     no hand-off barriers.  Loads for the next 64-column chunk are issued before the current chunk is converted.
+//   * the A operand ring holds a full K = 256 operand (4 chunks x [128 x 64] hi|lo = 128 KB).  Because a layer's epilogue
+//     starts only when that layer's MMAs have completed, every operand slot is known to be free when the epilogue refills
+//     it: the workers never wait for an "empty" barrier (except when a stage-0 operand is wider than the ring).
+//   * per tile a worker waits on 1 barrier per layer (accumulator complete) and arrives on 1 per produced chunk, one
+//     elected lane per warp.
+//   * the stage-0 operand of the NEXT tile is assembled between the last layer's accumulator-complete wait and its epilogue,
+//     so the tensor pipe runs the next tile's first layer under the LayerNorm epilogue of this tile.
+//   * warp 16: weight producer (cp.async.bulk of pre-swizzled 32 KB panels), warp 17: MMA issuer (one thread).
+// TMEM: 512 columns = two 128x256 fp32 accumulators alternating by layer.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gw_internal.h"
+#include "gw_ops.h"
+#include "gw_tc_ptx.cuh"
+
+namespace gw {
+namespace t3 {
+
+#ifdef GW_ABLATE
+#define ABL3(bit) ((ch.ablate & (bit)) != 0)
+#else
+#define ABL3(bit) false
+#endif
+enum { ABL_FENCE = 1, ABL_LOADS = 2, ABL_CONVERT = 4, ABL_STORES = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
+
+constexpr int TILE_M = 128;
+constexpr int A_SLOTS = 4, B_STAGES = 2;
+constexpr int A_HALF_BYTES = TILE_M * 128;      // [128 rows x 64 halfs]
+constexpr int A_SLOT_BYTES = 2 * A_HALF_BYTES;  // hi | lo
+constexpr int B_STAGE_BYTES = 256 * 128;        // [256 rows x 64 halfs], hi OR lo panel
+constexpr int WSPLIT = 4;                       // worker warps per TMEM lane quadrant; each owns 16 columns of every 64-column chunk
+constexpr int WORKER_WARPS = 4 * WSPLIT, NUM_WORKERS = 32 * WORKER_WARPS;
+constexpr int WARP_PRODUCER = WORKER_WARPS, WARP_MMA = WORKER_WARPS + 1;
+constexpr int NUM_THREADS = NUM_WORKERS + 128;  // + one auxiliary warpgroup: producer, MMA issuer, two idle warps
+constexpr int WORKER_REGS = 104, AUX_REGS = 56;  // setmaxnreg: 4 x 32 x 120 + 32 x 32 = 16384 registers per SM sub-partition
+constexpr int PAR_LAYERS = 6;
+constexpr int OFF_A = 0;
+constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
+constexpr int OFF_BAR = OFF_B + B_STAGES * B_STAGE_BYTES;
+constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4;
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int OFF_PAR = OFF_TMEM + 16;                // float bias[PAR_LAYERS][256]
+constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;  // float gamma_beta[2][2][256]
+constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_x[WSPLIT][128], ln_y[WSPLIT][128]: row statistics exchange
+constexpr int SMEM_BYTES = OFF_LN + 2 * WSPLIT * 128 * 4;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
+
+// tcgen05.ld 16 lanes x 256 bit, x2: 16 accumulator columns of 16 rows.  Lane t holds (cute SM100_TMEM_LOAD_16dp256b2x):
+//   r0,r1 = (row t/4    , cols 2(t%4)+{0,1})      r2,r3 = (row t/4 + 8, same cols)
+//   r4,r5 = (row t/4    , cols 8+2(t%4)+{0,1})    r6,r7 = (row t/4 + 8, same cols)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// A worker thread's fragment of one 64-column chunk: 16 values, index i = 8g + 4j + 2m + e
+//   tile row  r(k) = 32 q + 16 g + lane/4 + 8 m   (k = 2g + m),   chunk column = 16 hq + 8 j + 2 (lane%4) + e
+__device__ __forceinline__ bool vec2_ok(const float* base, int ld) { return ((reinterpret_cast<uintptr_t>(base) & 7) == 0) && ((ld & 1) == 0); }
+__device__ __forceinline__ bool src_gathered(int kind) { return kind == SRC_GATHER || kind == SRC_BGATHER || kind == SRC_GATHER_BCAST_RELU; }
+__device__ __forceinline__ bool src_per_sample(int kind) { return kind == SRC_STREAM || kind == SRC_GATHER || kind == SRC_GATHER_BCAST_RELU; }
+
+// source rows of my four tile rows (gather indices are the only per-tile state a source needs in registers; everything
+// else is re-read from the kernel parameters where it is used)
+__device__ __forceinline__ void rows_of(const RowSrc& s, int i0, const int (&rl)[4], int (&ri)[4]) {
+  const bool g = src_gathered(s.kind);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ri[k] = g ? __ldg(s.idx + i0 + rl[k]) : i0 + rl[k];
+}
+// my 16 values of the chunk whose first column relative to the source is `col` (includes 16hq + 2(lane%4)).  Warp-uniform
+// fast path: the warp's 16 columns lie inside the source and 8-byte loads are legal -> 8 independent LDG.64 in flight;
+// otherwise bounds-checked scalar loads (the 102-wide features, 78-wide outputs).
+__device__ __forceinline__ void load16(const float* base, int ld, int width, const int (&ri)[4], int col, int lc, float (&o)[16]) {
+  if (vec2_ok(base, ld) && (col - 2 * lc + 16 <= width)) {
+    float2 t[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* rowp = base + (size_t)ri[k] * (size_t)ld + col;
+      t[2 * k] = __ldg(reinterpret_cast<const float2*>(rowp));
+      t[2 * k + 1] = __ldg(reinterpret_cast<const float2*>(rowp + 8));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1);
+        o[i] = t[2 * k + j].x, o[i + 1] = t[2 * k + j].y;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* rowp = base + (size_t)ri[k] * (size_t)ld;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 8 * j;
+        o[i] = (c < width) ? __ldg(rowp + c) : 0.f;
+        o[i + 1] = (c + 1 < width) ? __ldg(rowp + c + 1) : 0.f;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void load16(const RowSrc& s, int b, const int (&ri)[4], int col, int lc, float (&o)[16]) {
+  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
+  load16(base, s.ld, s.width, ri, col, lc, o);
+}
+
+// Split my 16 values into fp16 hi/lo (or bf16) and store them into the swizzled K-major operand slot: row r, logical
+// 16-byte chunk c16 = 2hq + j lives at chunk position c16 ^ (r & 7); my two halfs sit at byte 4 (lane%4) of the chunk.
+__device__ __forceinline__ void store_operand16(uint8_t* slot, const int (&rt)[4], int hq, int lc, const float (&v)[16], bool split,
+                                                float& amax) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int r = rt[2 * g + m];
+      uint8_t* row_hi = slot + r * 128 + 4 * lc;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float a0 = v[8 * g + 4 * j + 2 * m], a1 = v[8 * g + 4 * j + 2 * m + 1];
+        amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+        const int pos = ((2 * hq + j) ^ (r & 7)) << 4;
+        if (split) {
+          const __half2 hh = __floats2half2_rn(a0, a1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          *reinterpret_cast<__half2*>(row_hi + pos) = hh;
+          *reinterpret_cast<__half2*>(row_hi + A_HALF_BYTES + pos) = ll;
+        } else {
+          *reinterpret_cast<__nv_bfloat162*>(row_hi + pos) = __floats2bfloat162_rn(a0, a1);
+        }
+      }
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __grid_constant__ TcChain ch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = ch.rows_per_sample, batch = ch.batch;
+  const int tiles_per_sample = (rows + TILE_M - 1) / TILE_M;
+  const int num_tiles = tiles_per_sample * batch;  // batch-major: tile -> (sample = tile % batch, row block = tile / batch)
+  const bool split = ch.split != 0;
+  const int parts = split ? 2 : 1;
+
+  const uint32_t bar_full_a = sbase + OFF_BAR;             // [A_SLOTS] workers -> MMA (one arrival per worker warp)
+  const uint32_t bar_empty_a = bar_full_a + 8 * A_SLOTS;   // [A_SLOTS] MMA -> workers (tcgen05.commit); waited only when stage 0 wraps the ring
+  const uint32_t bar_full_b = bar_empty_a + 8 * A_SLOTS;   // [B_STAGES] bulk copy -> MMA
+  const uint32_t bar_empty_b = bar_full_b + 8 * B_STAGES;  // [B_STAGES] MMA -> producer
+  const uint32_t bar_full_d = bar_empty_b + 8 * B_STAGES;  // [2] MMA -> workers: accumulator complete
+  const uint32_t bar_empty_d = bar_full_d + 16;            // [2] workers -> MMA: accumulator drained
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) {  // SWIZZLE_128B operand tiles must be 1 KB aligned
+      if (ch.status) atomicOr(ch.status, 4);
+      __trap();
+    }
+    for (int i = 0; i < A_SLOTS; ++i) mbar_init(bar_full_a + 8 * i, WORKER_WARPS), mbar_init(bar_empty_a + 8 * i, 1);
+    for (int i = 0; i < B_STAGES; ++i) mbar_init(bar_full_b + 8 * i, 1), mbar_init(bar_empty_b + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_full_d + 8 * i, 1), mbar_init(bar_empty_d + 8 * i, WORKER_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == WARP_MMA) {  // TMEM: all 512 columns (two fp32 accumulators of 256 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // per-layer column parameters -> shared memory (zero beyond n_valid)
+    float* par = reinterpret_cast<float*>(smem + OFF_PAR);
+    float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
+    int ln_slot = 0;
+    for (int l = 0; l < ch.n_layers; ++l) {
+      const TcLayer& L = ch.layer[l];
+      for (int c = threadIdx.x; c < 256; c += NUM_THREADS) par[l * 256 + c] = (L.bias && c < L.n_valid) ? __ldg(L.bias + c) : 0.f;
+      if (L.ln_g) {
+        for (int c = threadIdx.x; c < 256; c += NUM_THREADS) {
+          lnp[(ln_slot * 2 + 0) * 256 + c] = (c < L.n_valid) ? __ldg(L.ln_g + c) : 0.f;
+          lnp[(ln_slot * 2 + 1) * 256 + c] = (c < L.n_valid) ? __ldg(L.ln_b + c) : 0.f;
+        }
+        ++ln_slot;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // Register reallocation (inside each role's branch, so that ptxas budgets the roles separately): the auxiliary warpgroup
+  // keeps 32 registers per thread, the workers (which hold a 64-value LayerNorm fragment per thread) grow to 120.
+  if (warp >= WORKER_WARPS) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+  if (warp == WARP_PRODUCER) {
+    // ===================================== weight producer =========================================================
+    if (lane == 0) {
+      uint32_t bi = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < ch.n_layers; ++l) {
+          const TcLayer& L = ch.layer[l];
+          const uint32_t panel = (uint32_t)L.N * 128u;
+          const uint8_t* w = static_cast<const uint8_t*>(L.Wp);
+          const int nk = L.K >> 6;
+          for (int kc = 0; kc < nk; ++kc) {
+            for (int part = 0; part < parts; ++part, ++bi) {
+              const uint32_t stage = bi % B_STAGES, n = bi / B_STAGES;
+              mbar_wait(bar_empty_b + 8 * stage, (n & 1) ^ 1, ch.status);
+              if (ABL3(ABL_WEIGHTS)) {
+                mbar_arrive(bar_full_b + 8 * stage);
+                continue;
+              }
+              mbar_expect_tx(bar_full_b + 8 * stage, panel);
+              bulk_g2s(sbase + OFF_B + stage * B_STAGE_BYTES, w + (size_t)(kc * parts + part) * panel, panel, bar_full_b + 8 * stage);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================================== MMA issuer ==============================================================
+    if (lane == 0) {
+      uint32_t bi = 0, fi = 0, li = 0;
+      Tracer tr;
+      tr.init(ch.trace, 1, true);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t prev_first = fi;
+        tr.ev(1000);
+        for (int l = 0; l < ch.n_layers; ++l, ++li) {
+          const TcLayer& L = ch.layer[l];
+          const int nk = L.K >> 6;
+          const uint32_t idesc = umma_idesc(L.N, !split);
+          const uint32_t acc = li & 1, use = li >> 1;
+          tr.ev(100 + l);
+          mbar_wait(bar_empty_d + 8 * acc, (use & 1) ^ 1, ch.status);  // epilogue of layer li-2 has drained this accumulator
+          tc_fence_after();
+          tr.ev(110 + l);
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          const uint32_t first = L.reuse_a ? prev_first : fi;
+          const bool last_use = !(l + 1 < ch.n_layers && ch.layer[l + 1].reuse_a);
+          for (int kc = 0; kc < nk; ++kc) {
+            const uint32_t f = first + kc, slot = f % A_SLOTS, n = f / A_SLOTS;
+            mbar_wait(bar_full_a + 8 * slot, n & 1, ch.status);  // (already complete when the operand is re-used)
+            tc_fence_after();
+            tr.ev(200 + kc);
+            const uint32_t a_hi = sbase + OFF_A + slot * A_SLOT_BYTES, a_lo = a_hi + A_HALF_BYTES;
+            {  // hi weight panel: A_hi.B_hi (+ A_lo.B_hi)
+              const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
+              mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
+              tc_fence_after();
+              const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
+              if (!ABL3(ABL_MMA)) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, (kc | ks) != 0);
+                if (split) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_lo + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
+                }
+              }
+              tc_commit(bar_empty_b + 8 * stage);
+              ++bi;
+            }
+            if (split) {  // lo weight panel: A_hi.B_lo
+              const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
+              mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
+              tc_fence_after();
+              const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
+              if (!ABL3(ABL_MMA)) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, umma_desc(a_hi + 32 * ks), umma_desc(b + 32 * ks), idesc, 1);
+              }
+              tc_commit(bar_empty_b + 8 * stage);
+              ++bi;
+            }
+            if (last_use) tc_commit(bar_empty_a + 8 * slot);  // one phase per use of the slot
+            tr.ev(300 + kc);
+          }
+          tc_commit(bar_full_d + 8 * acc);  // accumulator complete -> epilogue
+          if (!L.reuse_a) {
+            prev_first = fi;
+            fi += nk;
+          }
+        }
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
+    // ===================================== workers =================================================================
+    const int q = warp & 3;    // TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..+31)
+    const int hq = warp >> 2;  // which 16 columns of every 64-column chunk
+    const int lr = lane >> 2, lc = lane & 3;
+    int rt[4];  // my four tile rows (= TMEM lanes)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rt[k] = 32 * q + 16 * (k >> 1) + lr + 8 * (k & 1);
+    const int cofs = 16 * hq + 2 * lc;  // my first column inside a 64-column chunk
+    float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
+    float* ln_y = ln_x + WSPLIT * 128;
+    uint32_t fi = 0, li = 0;
+    float amax = 0.f;
+    Tracer tr;
+    tr.init(ch.trace, 5 + (hq & 1), q == 0 && lane == 0 && hq < 2);
+
+    // publish one finished operand chunk: my writes -> async proxy, then one arrival per warp
+    auto publish = [&](uint32_t slot) {
+      if (!ABL3(ABL_FENCE)) fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full_a + 8 * slot);
+    };
+
+    // ---- stage 0: assemble the fp16 hi/lo operand of the first layer straight from global memory -----------------------
+    auto stage0 = [&](int tile) {
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      int rl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+      const int nk0 = ch.K0 >> 6, w0 = ch.a0[0].width;
+      int ri[4], ri2[4];  // rows of the current source (and of its broadcast partner)
+      int cur_src = -1;
+      auto fetch = [&](int c, float (&o)[16]) {
+        const int colc = 64 * c;
+        const int which = colc < w0 ? 0 : 1;
+        const RowSrc& src = ch.a0[which];
+        const int rel = which ? colc - w0 : colc;
+        if (src.kind == SRC_NONE || rel >= src.width || ABL3(ABL_LOADS)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = 0.f;
+          return;
+        }
+        if (which != cur_src) {
+          rows_of(src, i0, rl, ri);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ri2[k] = i0 + rl[k];
+          cur_src = which;
+        }
+        load16(src, bs, ri, rel + cofs, lc, o);
+        if (src.kind == SRC_GATHER_BCAST_RELU) {
+          float t[16];
+          load16(src.base2, src.ld2, src.width, ri2, rel + cofs, lc, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
+        }
+      };
+      float cur[16], nxt[16];
+      fetch(0, cur);
+      for (int c = 0; c < nk0; ++c) {
+        if (c + 1 < nk0) fetch(c + 1, nxt);
+        const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
+        if (c >= A_SLOTS) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // operand wider than the ring
+        if (!ABL3(ABL_CONVERT)) store_operand16(smem + OFF_A + slot * A_SLOT_BYTES, rt, hq, lc, cur, split, amax);
+        publish(slot);
+        tr.ev(500 + c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+      }
+      fi += nk0;
+    };
+
+    const int n_layers = ch.n_layers;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, first_tile = false) {
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      const int next_tile = tile + gridDim.x;
+      int rl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+      int ln_slot = 0;
+      // l == -1 (first tile only): this tile's own stage 0.  Afterwards stage 0 of tile t+1 runs inside tile t's last layer.
+      for (int l = first_tile ? -1 : 0; l < n_layers; ++l) {
+        const uint32_t acc = li & 1, use = li >> 1;
+        const bool last_layer = l + 1 == n_layers;
+        if (l < 0 || last_layer) {
+          if (l >= 0) {
+            // Every MMA of this tile has completed once this accumulator is full, so the whole operand ring is free:
+            // build the next tile's first operand now and let its first layer run on the other accumulator while this
+            // tile's last epilogue is computed.  (Before any per-layer state is live: the assembly needs the registers.)
+            tr.ev(600 + l);
+            mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+            tc_fence_after();
+            tr.ev(610 + l);
+          }
+          const int t = l < 0 ? tile : next_tile;
+          if (t < num_tiles) stage0(t);
+          if (l < 0) continue;
+        }
+        const TcLayer& L = ch.layer[l];
+        const int N = L.N, nval = L.n_valid;
+        const int np = (N + 63) >> 6;
+        const float wsi = L.wscale_inv;
+        const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
+        const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
+        const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
+        const bool relu = L.relu != 0, has_ln = L.ln_g != nullptr, feeds = L.feeds_next != 0;
+        const uint32_t g_o = OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_o = g_o + 1024;
+        if (has_ln) ++ln_slot;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
+
+        // Epilogue operands that come from global memory, prefetched one chunk ahead into pf0 / pf1:
+        //   pf0 = addend 0 (before the activation) or, on layers without addends, the residual (after LayerNorm); pf1 = addend 1
+        const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
+        const bool has0 = has_add0 || has_res;
+        int r0[4], r1[4];
+        float pf0[16], pf1[16];
+        auto prefetch = [&](int s) {
+          if (64 * s + 16 * hq >= N || ABL3(ABL_LOADS)) return;
+          if (has0) load16(src0, bs, r0, 64 * s + cofs, lc, pf0);
+          if (has_add1) load16(L.add[1], bs, r1, 64 * s + cofs, lc, pf1);
+        };
+        if (has0) rows_of(src0, i0, rl, r0);
+        if (has_add1) rows_of(L.add[1], i0, rl, r1);
+        prefetch(0);
+        if (!last_layer) {
+          tr.ev(600 + l);
+          mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+          tc_fence_after();
+          tr.ev(610 + l);
+        }
+
+        // LayerNorm statistics (first pass over the accumulator).  Each thread reduces its 16 columns of each of its 4 rows
+        // around a pivot (the row's first value it sees), the partial (mean, M2) pairs are merged with Chan's formula over
+        // the 4 lanes and 4 warps that share a row: one pass, no cancellation, one barrier.
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+        if (has_ln && !ABL3(ABL_LN)) {
+          float pv[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          int cnt = 0;
+          for (int s = 0; s < np; ++s) {
+            if (64 * s + 16 * hq >= N) break;
+            float v[16];
+            tmem_ld_16x256b_x2(taddr + 64 * s, v);
+            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+            tmem_wait_ld();
+            const float2 b0 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s);
+            const float2 b1 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s + 32);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 bb = ((i >> 2) & 1) ? b1 : b0;
+              v[i] = fmaf(v[i], wsi, (i & 1) ? bb.y : bb.x);
+            }
+            if (s == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int k = 2 * (i >> 3) + ((i >> 1) & 1);
+              const float d = v[i] - pv[k];
+              s1[k] += d;
+              s2[k] = fmaf(d, d, s2[k]);
+            }
+            cnt += 4;
+          }
+          float m2[4];
+          const float fc = (float)cnt, ic = cnt > 0 ? 1.0f / fc : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a = s1[k] * ic;
+            mean[k] = pv[k] + a;
+            m2[k] = fmaxf(s2[k] - s1[k] * a, 0.f);
+          }
+          float nn = fc;  // values per partial; the four lanes of a row hold equally many
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float mb = __shfl_xor_sync(0xffffffffu, mean[k], o), qb = __shfl_xor_sync(0xffffffffu, m2[k], o);
+              const float d = mb - mean[k];
+              mean[k] = 0.5f * (mean[k] + mb);
+              m2[k] = (m2[k] + qb) + d * d * (0.5f * nn);
+            }
+            nn *= 2.f;
+          }
+          if (lc == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float n = 0.f, mu = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WSPLIT; ++w) {  // same order in every thread of the row
+              const int cw = (N - 16 * w + 63) >> 6;  // chunks in which warp w owns columns
+              const float nw = cw > 0 ? 16.f * (float)cw : 0.f;
+              if (nw > 0.f) {
+                const float mw = ln_x[w * 128 + rt[k]], qw = ln_y[w * 128 + rt[k]];
+                const float d = mw - mu, nt = n + nw;
+                mu += d * (nw / nt);
+                q2 += qw + d * d * (n * nw / nt);
+                n = nt;
+              }
+            }
+            mean[k] = mu;
+            rstd[k] = 1.0f / sqrtf(q2 / (float)nval + 1e-5f);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
+        }
+
+        for (int s = 0; s < np; ++s) {
+          const bool have = 64 * s + 16 * hq < N;  // warp-uniform
+          const int col = 64 * s + cofs;
+          float v[16];
+          if (have && !ABL3(ABL_TMEM)) {
+            tmem_ld_16x256b_x2(taddr + 64 * s, v);
+            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+            tmem_wait_ld();
+            const float2 b0 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s);
+            const float2 b1 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s + 32);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 bb = ((i >> 2) & 1) ? b1 : b0;
+              v[i] = fmaf(v[i], wsi, (i & 1) ? bb.y : bb.x);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          if (s + 1 == np) {  // my last read of this accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
+          }
+          if (have) {
+            const bool ld_ok = !ABL3(ABL_LOADS);
+            if (has_add0 && ld_ok) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            }
+            if (has_add1 && ld_ok) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pf1[i];
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (has_ln) {
+              const float2 g0 = *reinterpret_cast<const float2*>(smem + g_o + 256 * s);
+              const float2 g1 = *reinterpret_cast<const float2*>(smem + g_o + 256 * s + 32);
+              const float2 e0 = *reinterpret_cast<const float2*>(smem + b_o + 256 * s);
+              const float2 e1 = *reinterpret_cast<const float2*>(smem + b_o + 256 * s + 32);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int k = 2 * (i >> 3) + ((i >> 1) & 1);
+                const float2 gg = ((i >> 2) & 1) ? g1 : g0, ee = ((i >> 2) & 1) ? e1 : e0;
+                v[i] = fmaf((v[i] - mean[k]) * rstd[k], (i & 1) ? gg.y : gg.x, (i & 1) ? ee.y : ee.x);
+              }
+            }
+            if (!has_add0 && has_res && ld_ok) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            }
+          }
+          if (s + 1 < np) prefetch(s + 1);  // in flight while this chunk is converted and stored
+          if (have) {
+            if (nval < N) {  // padded output columns (e.g. 78 of 80) must stay exactly zero
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col + 8 * ((i >> 2) & 1) + (i & 1) >= nval) v[i] = 0.f;
+            }
+            if (has_out && !ABL3(ABL_STORES)) {
+              float* ob = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo + col;
+              if (vec2_ok(ob - col, L.ldo) && 64 * s + 16 * hq + 16 <= L.out_cols) {  // warp-uniform: 8 STG.64, full sectors
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (rt[k] < nvalid) {
+                    float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
+                    const int i = 8 * (k >> 1) + 2 * (k & 1);
+                    *reinterpret_cast<float2*>(orow) = make_float2(v[i], v[i + 1]);
+                    *reinterpret_cast<float2*>(orow + 8) = make_float2(v[i + 4], v[i + 5]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (rt[k] < nvalid) {
+                    float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 8 * j;
+                      if (c < L.out_cols) orow[8 * j] = v[i];
+                      if (c + 1 < L.out_cols) orow[8 * j + 1] = v[i + 1];
+                    }
+                  }
+                }
+              }
+            }
+          }
+          if (feeds) {
+            const uint32_t slot = (fi + s) % A_SLOTS;
+            if (!ABL3(ABL_CONVERT)) store_operand16(smem + OFF_A + slot * A_SLOT_BYTES, rt, hq, lc, v, split, amax);
+            publish(slot);
+          }
+          tr.ev(700 + 10 * l + s);
+        }
+        if (feeds) fi += np;
+        ++li;
+        tr.ev(900 + l);
+      }
+    }
+    if (split && ch.status && amax > 60000.f) atomicOr(ch.status, 1);  // operand left the fp16 range: results invalid
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace t3
+
+cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream) {
+  using namespace t3;
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (num_sms[dev] == 0) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gw_chain_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    num_sms[dev] = n;
+  }
+  const long long R = (long long)ch.rows_per_sample * ch.batch;
+  if (R <= 0 || ch.n_layers <= 0) return cudaSuccess;
+  // structural requirements of the kernel
+  if (ch.n_layers > PAR_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
+  int n_ln = 0;
+  if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 63)) return cudaErrorInvalidValue;  // a chunk never straddles two sources
+  if (ch.layer[ch.n_layers - 1].feeds_next) return cudaErrorInvalidValue;
+  for (int a = 0; a < 2; ++a)
+    if (ch.a0[a].kind == SRC_SEGSUM) return cudaErrorInvalidValue;  // reduce with gw_segsum_kernel first
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const TcLayer& L = ch.layer[l];
+    if (!L.Wp || (L.K & 63) || (L.N & 15) || L.N > 256 || L.N <= 0 || L.n_valid <= 0 || L.n_valid > L.N) return cudaErrorInvalidValue;
+    if (L.feeds_next && (L.N & 63)) return cudaErrorInvalidValue;
+    if (L.ln_g && L.add[0].kind != SRC_NONE) return cudaErrorInvalidValue;  // addends are applied before ReLU, not before LayerNorm
+    if (L.ln_g && (L.n_valid != L.N || ++n_ln > 2)) return cudaErrorInvalidValue;
+    if (L.add[0].kind == SRC_NONE && L.add[1].kind != SRC_NONE) return cudaErrorInvalidValue;
+    for (int a = 0; a < 2; ++a)
+      if (L.add[a].kind != SRC_NONE && L.add[a].kind != SRC_STREAM && L.add[a].kind != SRC_BCAST && L.add[a].kind != SRC_GATHER &&
+          L.add[a].kind != SRC_BGATHER)
+        return cudaErrorInvalidValue;
+    if (L.residual.kind != SRC_NONE && L.residual.kind != SRC_STREAM && L.residual.kind != SRC_BCAST && L.residual.kind != SRC_GATHER &&
+        L.residual.kind != SRC_BGATHER)
+      return cudaErrorInvalidValue;
+    if (L.add[0].kind != SRC_NONE && L.residual.kind != SRC_NONE) return cudaErrorInvalidValue;  // they share the prefetch registers
+    if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
+    if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;
+    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next || L.K > 64 * A_SLOTS)) return cudaErrorInvalidValue;  // the whole operand must still be resident
+  }
+  const int tiles = ((ch.rows_per_sample + TILE_M - 1) / TILE_M) * ch.batch;
+  const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+  gw_chain_tc3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gw
