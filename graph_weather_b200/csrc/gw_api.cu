@@ -222,6 +222,10 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
   return 0;
 }
 
+int tc_generation() {
+  static const int gen = getenv("GW_TC_KERNEL") ? atoi(getenv("GW_TC_KERNEL")) : 3;
+  return gen == 2 ? 2 : 3;
+}
 static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
   ch.status = p->tc_status_dev;
@@ -238,8 +242,7 @@ static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   cudaError_t e;
   {
     TimedLaunch t(p, st);
-    static const int gen = getenv("GW_TC_KERNEL") ? atoi(getenv("GW_TC_KERNEL")) : 2;
-    e = gen == 2 ? launch_chain_tc(ch, st) : launch_chain_tc3(ch, st);
+    e = tc_generation() == 2 ? launch_chain_tc(ch, st) : launch_chain_tc3(ch, st);
   }
   if (e != cudaSuccess) {
     set_error(std::string("tensor-core chain launch failed: ") + cudaGetErrorString(e));
@@ -449,7 +452,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
       scale = std::ldexp(1.f, 12 - e);   // amax * scale in [2048, 4096)
     }
     void* dst = p->tc_packed.p + off;
-    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, dst, st));
+    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, tc_generation() == 3 ? 1 : 0, dst, st));
     reqs[i].out->p = dst;
     reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
     reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;

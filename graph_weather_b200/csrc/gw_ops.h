@@ -81,6 +81,7 @@ struct TcChain {
   int32_t split = 1;          // 1: fp16 hi+lo operands, 3 MMAs per product (fp32-faithful); 0: bf16 single MMA
   int32_t* status = nullptr;  // device word: bit0 = operand exceeded the fp16 range, bit1 = pipeline timeout
   long long* trace = nullptr; // optional debug timeline: [8 roles][1024 events][2] = {clock64, code}; CTA 0 only
+  int32_t fast = 0;           // gw_tc3: bit l = layer l takes the lean full-width path, bit 31 = stage 0 does (set by the launcher)
   int32_t ablate = 0;         // diagnostics build only (-DGW_ABLATE): bit mask of pipeline parts to skip, for timing attribution
   TcLayer layer[TC_MAX_LAYERS];
 };

@@ -790,12 +790,16 @@ size_t tc_packed_bytes(int K_src, int N_src, int parts) {
 }
 
 // dst image: for chunk kc, part p: panel of N rows x 128 B; element (n, k): 16B chunk ((k%64)/8) ^ (n&7), half k%8
+// perm16 (gw_tc3.cu): inside every group of 16 output rows and of 16 K columns, packed position a holds logical index
+// f(a) = 4*((a>>1)&3) + 2*(a>>3) + (a&1), the order in which a tcgen05.ld.16x256b fragment gives each thread 4 consecutive features.
+__host__ __device__ inline int perm16_f(int a) { return (a & ~15) | (4 * ((a >> 1) & 3) + 2 * ((a >> 3) & 1) + (a & 1)); }
 __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int K_src, int N_src, int Kp, int Np,
-                                       float wscale, int parts, uint8_t* __restrict__ dst) {
+                                       float wscale, int parts, int perm16, uint8_t* __restrict__ dst) {
   const size_t total = (size_t)Np * Kp;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(e / Kp), k = (int)(e % Kp);
-    const float w = (n < N_src && k < K_src) ? W[(size_t)n * ldw + k] * wscale : 0.f;
+    const int ns = perm16 ? perm16_f(n) : n, ks = perm16 ? perm16_f(k) : k;
+    const float w = (ns < N_src && ks < K_src) ? W[(size_t)ns * ldw + ks] * wscale : 0.f;
     const int kc = k >> 6, kk = k & 63;
     const size_t panel = (size_t)Np * 128;
     const size_t off = (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + ((kk & 7) << 1));
@@ -810,10 +814,10 @@ __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int
   }
 }
 
-cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, void* dst,
+cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm16, void* dst,
                                 cudaStream_t stream) {
   const int Kp = round_up(K_src, 64), Np = round_up(N_src, 16);
-  gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, static_cast<uint8_t*>(dst));
+  gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, perm16, static_cast<uint8_t*>(dst));
   count_launch();
   return cudaGetLastError();
 }

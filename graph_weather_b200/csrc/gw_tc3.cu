@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gw_internal.h"
 #include "gw_ops.h"
@@ -85,7 +86,11 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // A worker thread's fragment of one 64-column chunk: 16 values, index i = 8g + 4j + 2m + e
-//   tile row  r(k) = 32 q + 16 g + lane/4 + 8 m   (k = 2g + m),   chunk column = 16 hq + 8 j + 2 (lane%4) + e
+//   tile row  r(k) = 32 q + 16 g + lane/4 + 8 m   (k = 2g + m),   accumulator column = 16 hq + 8 j + 2 (lane%4) + e
+// The weights are packed with their output rows AND K columns permuted inside every group of 16 (perm16, gw_tc.cu) so that
+// accumulator column 8j + 2(lane%4) + e holds LOGICAL feature 4 (lane%4) + 2j + e: a thread owns 4 consecutive features of a row
+// (16 bytes of fp32) -> global loads / stores are 128-bit, four adjacent lanes cover 64 B of one row.  Operands live in shared
+// memory in accumulator order on both sides of every product, so nothing else changes.
 __device__ __forceinline__ bool vec2_ok(const float* base, int ld) { return ((reinterpret_cast<uintptr_t>(base) & 7) == 0) && ((ld & 1) == 0); }
 __device__ __forceinline__ bool src_gathered(int kind) { return kind == SRC_GATHER || kind == SRC_BGATHER || kind == SRC_GATHER_BCAST_RELU; }
 __device__ __forceinline__ bool src_per_sample(int kind) { return kind == SRC_STREAM || kind == SRC_GATHER || kind == SRC_GATHER_BCAST_RELU; }
@@ -97,32 +102,41 @@ __device__ __forceinline__ void rows_of(const RowSrc& s, int i0, const int (&rl)
 #pragma unroll
   for (int k = 0; k < 4; ++k) ri[k] = g ? __ldg(s.idx + i0 + rl[k]) : i0 + rl[k];
 }
-// my 16 values of the chunk whose first column relative to the source is `col` (includes 16hq + 2(lane%4)).  Warp-uniform
-// fast path: the warp's 16 columns lie inside the source and 8-byte loads are legal -> 8 independent LDG.64 in flight;
-// otherwise bounds-checked scalar loads (the 102-wide features, 78-wide outputs).
+// my 16 values (4 rows x logical columns col .. col+3; `col` includes 16hq + 4(lane%4)).  Warp-uniform tiers: 128-bit loads when
+// the warp's 16 columns lie inside the source and rows are 16-byte aligned, 64-bit when 8-byte aligned (the 102-wide
+// features), else bounds-checked scalars.
+__device__ __forceinline__ bool vec4_ok(const float* base, int ld) { return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0); }
 __device__ __forceinline__ void load16(const float* base, int ld, int width, const int (&ri)[4], int col, int lc, float (&o)[16]) {
-  if (vec2_ok(base, ld) && (col - 2 * lc + 16 <= width)) {
+  const bool inside = col - 4 * lc + 16 <= width;
+  if (inside && vec4_ok(base, ld)) {
+    float4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(base + (size_t)ri[k] * (size_t)ld + col));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 8 * (k >> 1) + 2 * (k & 1);
+      o[i] = t[k].x, o[i + 1] = t[k].y, o[i + 4] = t[k].z, o[i + 5] = t[k].w;
+    }
+  } else if (inside && vec2_ok(base, ld)) {
     float2 t[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float* rowp = base + (size_t)ri[k] * (size_t)ld + col;
       t[2 * k] = __ldg(reinterpret_cast<const float2*>(rowp));
-      t[2 * k + 1] = __ldg(reinterpret_cast<const float2*>(rowp + 8));
+      t[2 * k + 1] = __ldg(reinterpret_cast<const float2*>(rowp + 2));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1);
-        o[i] = t[2 * k + j].x, o[i + 1] = t[2 * k + j].y;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int i = 8 * (k >> 1) + 2 * (k & 1);
+      o[i] = t[2 * k].x, o[i + 1] = t[2 * k].y, o[i + 4] = t[2 * k + 1].x, o[i + 5] = t[2 * k + 1].y;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float* rowp = base + (size_t)ri[k] * (size_t)ld;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 8 * j;
+        const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 2 * j;
         o[i] = (c < width) ? __ldg(rowp + c) : 0.f;
         o[i + 1] = (c + 1 < width) ? __ldg(rowp + c + 1) : 0.f;
       }
@@ -162,6 +176,59 @@ __device__ __forceinline__ void store_operand16(uint8_t* slot, const int (&rt)[4
     }
 }
 
+
+// ---- lean full-width path --------------------------------------------------------------------------------------------
+// When every source / output of a layer is 8-byte aligned and at least as wide as the layer (the processor and decoder edge
+// and node passes: >95 % of the run time), row pointers are resolved once per layer and every access of the unrolled
+// 4-chunk loop is a single instruction with an immediate offset.
+__device__ __forceinline__ void row_ptrs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, const float* (&p)[4]) {
+  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0 + cofs;
+  const bool g = src_gathered(s.kind);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = g ? __ldg(s.idx + i0 + rl[k]) : i0 + rl[k];
+    p[k] = base + (size_t)row * (size_t)s.ld;
+  }
+}
+// my 16 values at float offset `off` from the row pointers (compile-time `off` folds into the instruction): 4 LDG.128
+__device__ __forceinline__ void ldfrag(const float* const (&p)[4], int off, float (&o)[16]) {
+  float4 t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(p[k] + off));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 8 * (k >> 1) + 2 * (k & 1);
+    o[i] = t[k].x, o[i + 1] = t[k].y, o[i + 4] = t[k].z, o[i + 5] = t[k].w;
+  }
+}
+// Operand store with precomputed addressing.  `sa` = shared address of (my row 32q + lane/4, my half2, chunk j = 0) inside the
+// slot; the j = 1 chunk is sa ^ 16 (SWIZZLE_128B flips bit 4), my other rows are +8 / +16 / +24 rows = immediates.
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <bool SPLIT>
+__device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)[16], float& amax) {
+  const uint32_t sa1 = sa ^ 16u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1);
+      const float a0 = v[i], a1 = v[i + 1];
+      amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+      const uint32_t addr = (j ? sa1 : sa) + (16 * (k >> 1) + 8 * (k & 1)) * 128;
+      if (SPLIT) {
+        const __half2 hh = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        sts32(addr, *reinterpret_cast<const uint32_t*>(&hh));
+        sts32(addr + A_HALF_BYTES, *reinterpret_cast<const uint32_t*>(&ll));
+      } else {
+        const __nv_bfloat162 bb = __floats2bfloat162_rn(a0, a1);
+        sts32(addr, *reinterpret_cast<const uint32_t*>(&bb));
+      }
+    }
+}
+
+template <bool SPLIT, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __grid_constant__ TcChain ch) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -169,8 +236,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
   const int rows = ch.rows_per_sample, batch = ch.batch;
   const int tiles_per_sample = (rows + TILE_M - 1) / TILE_M;
   const int num_tiles = tiles_per_sample * batch;  // batch-major: tile -> (sample = tile % batch, row block = tile / batch)
-  const bool split = ch.split != 0;
-  const int parts = split ? 2 : 1;
+  constexpr bool split = SPLIT;
+  constexpr int parts = SPLIT ? 2 : 1;
 
   const uint32_t bar_full_a = sbase + OFF_BAR;             // [A_SLOTS] workers -> MMA (one arrival per worker warp)
   const uint32_t bar_empty_a = bar_full_a + 8 * A_SLOTS;   // [A_SLOTS] MMA -> workers (tcgen05.commit); waited only when stage 0 wraps the ring
@@ -319,7 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     int rt[4];  // my four tile rows (= TMEM lanes)
 #pragma unroll
     for (int k = 0; k < 4; ++k) rt[k] = 32 * q + 16 * (k >> 1) + lr + 8 * (k & 1);
-    const int cofs = 16 * hq + 2 * lc;  // my first column inside a 64-column chunk
+    const int cofs = 16 * hq + 4 * lc;  // my first (logical) column inside a 64-column chunk; the operand position uses 2 * lc
     float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
     float* ln_y = ln_x + WSPLIT * 128;
     uint32_t fi = 0, li = 0;
@@ -383,6 +450,227 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       fi += nk0;
     };
 
+    // operand-store address of (my first row, chunk j = 0) inside a slot; see store_operand_fast
+    const uint32_t sa0 = sbase + OFF_A + (32 * q + lr) * 128 + 4 * lc + (((2 * hq) ^ lr) << 4);
+
+    // ---- stage 0, lean path: every 64-column chunk lies inside one aligned source -----------------------------------------
+    auto stage0_fast = [&](int tile) {
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      int rl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+      const int nk0 = ch.K0 >> 6, nc0 = ch.a0[0].width >> 6;
+      const float* pa[4];
+      const float* pb[4];
+      bool gbr = false;
+      auto setsrc = [&](const RowSrc& src) {
+        row_ptrs(src, bs, i0, rl, cofs, pa);
+        gbr = src.kind == SRC_GATHER_BCAST_RELU;
+        if (gbr) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pb[k] = src.base2 + (size_t)(i0 + rl[k]) * (size_t)src.ld2 + cofs;
+        }
+      };
+      auto fetch = [&](int c, float (&o)[16]) {
+        if (c == nc0) setsrc(ch.a0[1]);
+        const int off = 64 * (c < nc0 ? c : c - nc0);
+        if (ABL3(ABL_LOADS)) return;
+        ldfrag(pa, off, o);
+        if (gbr) {
+          float t[16];
+          ldfrag(pb, off, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
+        }
+      };
+      float cur[16], nxt[16];
+      setsrc(ch.a0[0]);
+      fetch(0, cur);
+      for (int c = 0; c < nk0; ++c) {
+        if (c + 1 < nk0) fetch(c + 1, nxt);
+        const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
+        if (c >= A_SLOTS) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // operand wider than the ring
+        if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
+        publish(slot);
+        tr.ev(500 + c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+      }
+      fi += nk0;
+    };
+
+    // ---- one layer's epilogue, lean path: N = 256, full-width aligned addends / residual / output ------------------------
+    // Register budget: v[16] + pf0[16] + aux[16] + two row-pointer sets.  `aux` is the add[1] prefetch or, on LayerNorm layers
+    // (which have no addends), the per-row scale/shift; `p1` is the add[1] rows or the output rows (never both: launcher).
+    auto layer_fast = [&](int l, uint32_t acc, uint32_t use, bool waited, int bs, int i0, int nvalid, int ln_slot) {
+      const TcLayer& L = ch.layer[l];
+      const float wsi = L.wscale_inv;
+      const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
+      const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
+      const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
+      const bool relu = L.relu != 0, has_ln = L.ln_g != nullptr, feeds = L.feeds_next != 0;
+      const uint32_t g_o = OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_o = g_o + 1024;
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
+      const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
+      const bool has0 = (has_add0 || has_res) && !ABL3(ABL_LOADS), has1 = has_add1 && !ABL3(ABL_LOADS);
+      const float* p0[4];
+      const float* p1[4];
+      float pf0[16], aux[16];
+      {
+        int rl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+        if (has0) row_ptrs(src0, bs, i0, rl, cofs, p0);
+        if (has1) row_ptrs(L.add[1], bs, i0, rl, cofs, p1);
+      }
+      if (has0) ldfrag(p0, 0, pf0);
+      if (has1) ldfrag(p1, 0, aux);
+      if (!waited) {
+        tr.ev(600 + l);
+        mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+        tc_fence_after();
+        tr.ev(610 + l);
+      }
+      if (has_ln) {  // LayerNorm as v * aux[k] + aux[4 + k] per row
+#pragma unroll
+        for (int k = 0; k < 4; ++k) aux[k] = 1.f, aux[4 + k] = 0.f;
+      }
+      if (has_ln && !ABL3(ABL_LN)) {
+        float pv[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          float v[16];
+          tmem_ld_16x256b_x2(taddr + 64 * s, v);
+          tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+          tmem_wait_ld();
+          const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
+          if (s == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = 2 * (i >> 3) + ((i >> 1) & 1);
+            const float d = v[i] - pv[k];
+            s1[k] += d;
+            s2[k] = fmaf(d, d, s2[k]);
+          }
+        }
+        float mean[4], m2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = s1[k] * (1.0f / 16.0f);
+          mean[k] = pv[k] + a;
+          m2[k] = fmaxf(s2[k] - s1[k] * a, 0.f);
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float mb = __shfl_xor_sync(0xffffffffu, mean[k], o), qb = __shfl_xor_sync(0xffffffffu, m2[k], o);
+            const float d = mb - mean[k];
+            mean[k] = 0.5f * (mean[k] + mb);
+            m2[k] = (m2[k] + qb) + d * d * (o == 1 ? 8.0f : 16.0f);
+          }
+        }
+        if (lc == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float n = 0.f, mu = 0.f, q2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < WSPLIT; ++w) {  // same order in every thread of the row; 64 values per warp partial
+            const float mw = ln_x[w * 128 + rt[k]], qw = ln_y[w * 128 + rt[k]];
+            const float d = mw - mu, nt = n + 64.f;
+            mu += d * (64.f / nt);
+            q2 += qw + d * d * (n * 64.f / nt);
+            n = nt;
+          }
+          const float rstd = 1.0f / sqrtf(q2 * (1.0f / 256.0f) + 1e-5f);
+          aux[k] = rstd, aux[4 + k] = -mu * rstd;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
+      }
+      if (has_out) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p1[k] = L.out + ((size_t)bs * rows + i0 + rt[k]) * (size_t)L.ldo + cofs;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float v[16];
+        if (!ABL3(ABL_TMEM)) {
+          tmem_ld_16x256b_x2(taddr + 64 * s, v);
+          tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (s == 3) {  // my last read of this accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
+        }
+        const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
+        if (has_add0 && has0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+        }
+        if (has1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += aux[i];
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (has_ln) {
+          const float4 g4 = *reinterpret_cast<const float4*>(smem + g_o + 256 * s);
+          const float4 e4 = *reinterpret_cast<const float4*>(smem + b_o + 256 * s);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = 2 * (i >> 3) + ((i >> 1) & 1);
+            const float gx = ((i >> 2) & 1) ? ((i & 1) ? g4.w : g4.z) : ((i & 1) ? g4.y : g4.x);
+            const float ex = ((i >> 2) & 1) ? ((i & 1) ? e4.w : e4.z) : ((i & 1) ? e4.y : e4.x);
+            v[i] = fmaf(fmaf(v[i], aux[k], aux[4 + k]), gx, ex);
+          }
+        }
+        if (!has_add0 && has0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+        }
+        if (s < 3) {  // next chunk's global operands: in flight while this chunk is stored / converted
+          if (has0) ldfrag(p0, 64 * (s + 1), pf0);
+          if (has1) ldfrag(p1, 64 * (s + 1), aux);
+        }
+        if (has_out && !ABL3(ABL_STORES)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (rt[k] < nvalid) {
+              const int i = 8 * (k >> 1) + 2 * (k & 1);
+              float* o = const_cast<float*>(p1[k]);
+              *reinterpret_cast<float4*>(o + 64 * s) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+            }
+          }
+        }
+        if (feeds) {
+          const uint32_t slot = (fi + s) % A_SLOTS;
+          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
+          publish(slot);
+        }
+        tr.ev(700 + 10 * l + s);
+      }
+      if (feeds) fi += 4;
+    };
+
     const int n_layers = ch.n_layers;
     bool first_tile = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, first_tile = false) {
@@ -408,17 +696,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             tr.ev(610 + l);
           }
           const int t = l < 0 ? tile : next_tile;
-          if (t < num_tiles) stage0(t);
+          if (t < num_tiles) {
+            if constexpr (FAST) stage0_fast(t); else stage0(t);
+          }
           if (l < 0) continue;
         }
         const TcLayer& L = ch.layer[l];
+        const bool has_ln = L.ln_g != nullptr;
+        if constexpr (FAST) {
+          layer_fast(l, acc, use, last_layer, bs, i0, nvalid, ln_slot);
+          if (has_ln) ++ln_slot;
+          ++li;
+          tr.ev(900 + l);
+          continue;
+        }
         const int N = L.N, nval = L.n_valid;
         const int np = (N + 63) >> 6;
         const float wsi = L.wscale_inv;
         const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
         const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
         const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
-        const bool relu = L.relu != 0, has_ln = L.ln_g != nullptr, feeds = L.feeds_next != 0;
+        const bool relu = L.relu != 0, feeds = L.feeds_next != 0;
         const uint32_t g_o = OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_o = g_o + 1024;
         if (has_ln) ++ln_slot;
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
@@ -457,13 +755,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             tmem_ld_16x256b_x2(taddr + 64 * s, v);
             tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
             tmem_wait_ld();
-            const float2 b0 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s);
-            const float2 b1 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s + 32);
+            const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 bb = ((i >> 2) & 1) ? b1 : b0;
-              v[i] = fmaf(v[i], wsi, (i & 1) ? bb.y : bb.x);
-            }
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
             if (s == 0) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
@@ -531,13 +825,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             tmem_ld_16x256b_x2(taddr + 64 * s, v);
             tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
             tmem_wait_ld();
-            const float2 b0 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s);
-            const float2 b1 = *reinterpret_cast<const float2*>(smem + bias_o + 256 * s + 32);
+            const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 bb = ((i >> 2) & 1) ? b1 : b0;
-              v[i] = fmaf(v[i], wsi, (i & 1) ? bb.y : bb.x);
-            }
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -562,15 +852,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             if (has_ln) {
-              const float2 g0 = *reinterpret_cast<const float2*>(smem + g_o + 256 * s);
-              const float2 g1 = *reinterpret_cast<const float2*>(smem + g_o + 256 * s + 32);
-              const float2 e0 = *reinterpret_cast<const float2*>(smem + b_o + 256 * s);
-              const float2 e1 = *reinterpret_cast<const float2*>(smem + b_o + 256 * s + 32);
+              const float4 g4 = *reinterpret_cast<const float4*>(smem + g_o + 256 * s);
+              const float4 e4 = *reinterpret_cast<const float4*>(smem + b_o + 256 * s);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int k = 2 * (i >> 3) + ((i >> 1) & 1);
-                const float2 gg = ((i >> 2) & 1) ? g1 : g0, ee = ((i >> 2) & 1) ? e1 : e0;
-                v[i] = fmaf((v[i] - mean[k]) * rstd[k], (i & 1) ? gg.y : gg.x, (i & 1) ? ee.y : ee.x);
+                const float gx = ((i >> 2) & 1) ? ((i & 1) ? g4.w : g4.z) : ((i & 1) ? g4.y : g4.x);
+                const float ex = ((i >> 2) & 1) ? ((i & 1) ? e4.w : e4.z) : ((i & 1) ? e4.y : e4.x);
+                v[i] = fmaf((v[i] - mean[k]) * rstd[k], gx, ex);
               }
             }
             if (!has_add0 && has_res && ld_ok) {
@@ -583,18 +872,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             if (nval < N) {  // padded output columns (e.g. 78 of 80) must stay exactly zero
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (col + 8 * ((i >> 2) & 1) + (i & 1) >= nval) v[i] = 0.f;
+                if (col + 2 * ((i >> 2) & 1) + (i & 1) >= nval) v[i] = 0.f;
             }
             if (has_out && !ABL3(ABL_STORES)) {
               float* ob = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo + col;
-              if (vec2_ok(ob - col, L.ldo) && 64 * s + 16 * hq + 16 <= L.out_cols) {  // warp-uniform: 8 STG.64, full sectors
+              const bool inside = 64 * s + 16 * hq + 16 <= L.out_cols;  // warp-uniform
+              if (inside && vec4_ok(ob - col, L.ldo)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (rt[k] < nvalid) {
+                    const int i = 8 * (k >> 1) + 2 * (k & 1);
+                    *reinterpret_cast<float4*>(ob + (size_t)rt[k] * (size_t)L.ldo) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+                  }
+                }
+              } else if (inside && vec2_ok(ob - col, L.ldo)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (rt[k] < nvalid) {
                     float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
                     const int i = 8 * (k >> 1) + 2 * (k & 1);
                     *reinterpret_cast<float2*>(orow) = make_float2(v[i], v[i + 1]);
-                    *reinterpret_cast<float2*>(orow + 8) = make_float2(v[i + 4], v[i + 5]);
+                    *reinterpret_cast<float2*>(orow + 2) = make_float2(v[i + 4], v[i + 5]);
                   }
                 }
               } else {
@@ -604,9 +902,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
                     float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                      const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 8 * j;
-                      if (c < L.out_cols) orow[8 * j] = v[i];
-                      if (c + 1 < L.out_cols) orow[8 * j + 1] = v[i + 1];
+                      const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 2 * j;
+                      if (c < L.out_cols) orow[2 * j] = v[i];
+                      if (c + 1 < L.out_cols) orow[2 * j + 1] = v[i + 1];
                     }
                   }
                 }
@@ -638,7 +936,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 
 }  // namespace t3
 
-cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream) {
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool simple_kind(int k) { return k == SRC_STREAM || k == SRC_BCAST || k == SRC_GATHER || k == SRC_BGATHER; }
+// a source every thread may read with 8-byte loads over `need` columns
+static bool src_fast(const RowSrc& s, int need) {
+  return simple_kind(s.kind) && s.width >= need && aligned16(s.base + s.col0) && !(s.ld & 3);
+}
+
+cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
+  TcChain ch = ch_in;
   using namespace t3;
   static int num_sms[64] = {0};
   int dev = 0;
@@ -649,8 +955,12 @@ cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream) {
     int n = 0;
     e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gw_chain_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    const void* fns[4] = {(const void*)gw_chain_tc3_kernel<true, true>, (const void*)gw_chain_tc3_kernel<true, false>,
+                          (const void*)gw_chain_tc3_kernel<false, true>, (const void*)gw_chain_tc3_kernel<false, false>};
+    for (int i = 0; i < 4; ++i) {
+      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+    }
     num_sms[dev] = n;
   }
   const long long R = (long long)ch.rows_per_sample * ch.batch;
@@ -683,7 +993,43 @@ cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream) {
   }
   const int tiles = ((ch.rows_per_sample + TILE_M - 1) / TILE_M) * ch.batch;
   const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
-  gw_chain_tc3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+  // which parts take the lean full-width path
+  ch.fast = 0;
+  {
+    bool ok = true;
+    int wsum = 0;
+    for (int a = 0; a < 2; ++a) {
+      const RowSrc& s = ch.a0[a];
+      if (s.kind == SRC_NONE) continue;
+      const bool gbr = s.kind == SRC_GATHER_BCAST_RELU;
+      ok = ok && (simple_kind(s.kind) || gbr) && !(s.width & 63) && aligned16(s.base + s.col0) && !(s.ld & 3);
+      if (gbr) ok = ok && aligned16(s.base2) && !(s.ld2 & 3);
+      wsum += s.width;
+    }
+    if (ok && wsum == ch.K0 && ch.a0[0].kind != SRC_NONE) ch.fast |= (int32_t)0x80000000u;
+  }
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const TcLayer& L = ch.layer[l];
+    bool ok = L.N == 256 && L.n_valid == 256;
+    for (int a = 0; a < 2; ++a)
+      if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], 256);
+    if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, 256);
+    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= 256 && L.add[1].kind == SRC_NONE;
+    if (ok) ch.fast |= 1 << l;
+  }
+  if (getenv("GW_TC3_NOFAST")) ch.fast = 0;
+  const bool all_fast = ch.fast == (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
+  if (ch.split) {
+    if (all_fast)
+      gw_chain_tc3_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+    else
+      gw_chain_tc3_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+  } else {
+    if (all_fast)
+      gw_chain_tc3_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+    else
+      gw_chain_tc3_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+  }
   count_launch();
   return cudaGetLastError();
 }
