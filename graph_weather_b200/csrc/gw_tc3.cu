@@ -48,6 +48,10 @@ namespace t3 {
 #endif
 enum { ABL_FENCE = 1, ABL_LOADS = 2, ABL_CONVERT = 4, ABL_STORES = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
 
+#ifndef GW_CHUNK_UNROLL
+#define GW_CHUNK_UNROLL 1  // the per-chunk loops stay rolled: unrolled, their code no longer fits the instruction cache
+#endif
+constexpr int CHUNK_UNROLL = GW_CHUNK_UNROLL;
 constexpr int TILE_M = 128;
 constexpr int A_SLOTS = 4, B_STAGES = 2;
 constexpr int A_HALF_BYTES = TILE_M * 128;      // [128 rows x 64 halfs]
@@ -178,23 +182,27 @@ __device__ __forceinline__ void store_operand16(uint8_t* slot, const int (&rt)[4
 
 
 // ---- lean full-width path --------------------------------------------------------------------------------------------
-// When every source / output of a layer is 8-byte aligned and at least as wide as the layer (the processor and decoder edge
-// and node passes: >95 % of the run time), row pointers are resolved once per layer and every access of the unrolled
-// 4-chunk loop is a single instruction with an immediate offset.
-__device__ __forceinline__ void row_ptrs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, const float* (&p)[4]) {
-  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0 + cofs;
-  const bool g = src_gathered(s.kind);
+// When every source / output of a layer is 16-byte aligned and at least as wide as the layer (the processor and decoder edge
+// and node passes: >95 % of the run time), a source is a warp-uniform 64-bit base plus four 32-bit byte offsets (one per row
+// of mine), resolved once per layer; every access is base + offset + immediate.  Contiguous sources are addressed relative
+// to the tile's first row, gathered ones relative to the sample (the launcher checks that this fits 32 bits).
+__device__ __forceinline__ const float* row_refs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, uint32_t (&off)[4]) {
+  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
+  if (src_gathered(s.kind)) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int row = g ? __ldg(s.idx + i0 + rl[k]) : i0 + rl[k];
-    p[k] = base + (size_t)row * (size_t)s.ld;
+    for (int k = 0; k < 4; ++k) off[k] = ((uint32_t)__ldg(s.idx + i0 + rl[k]) * (uint32_t)s.ld + (uint32_t)cofs) * 4u;
+    return base;
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) off[k] = ((uint32_t)rl[k] * (uint32_t)s.ld + (uint32_t)cofs) * 4u;
+  return base + (size_t)i0 * (size_t)s.ld;
 }
-// my 16 values at float offset `off` from the row pointers (compile-time `off` folds into the instruction): 4 LDG.128
-__device__ __forceinline__ void ldfrag(const float* const (&p)[4], int off, float (&o)[16]) {
+// my 16 values at float offset `coff` from the row references: 4 LDG.128
+__device__ __forceinline__ void ldfrag(const float* base, const uint32_t (&off)[4], int coff, float (&o)[16]) {
+  const char* b = reinterpret_cast<const char*>(base + coff);
   float4 t[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(p[k] + off));
+  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(b + off[k]));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = 8 * (k >> 1) + 2 * (k & 1);
@@ -461,25 +469,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
       for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
       const int nk0 = ch.K0 >> 6, nc0 = ch.a0[0].width >> 6;
-      const float* pa[4];
-      const float* pb[4];
+      const float* ba = nullptr;
+      const float* bb = nullptr;
+      uint32_t oa[4], ob[4];
       bool gbr = false;
       auto setsrc = [&](const RowSrc& src) {
-        row_ptrs(src, bs, i0, rl, cofs, pa);
+        ba = row_refs(src, bs, i0, rl, cofs, oa);
         gbr = src.kind == SRC_GATHER_BCAST_RELU;
         if (gbr) {
+          bb = src.base2 + (size_t)i0 * (size_t)src.ld2;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) pb[k] = src.base2 + (size_t)(i0 + rl[k]) * (size_t)src.ld2 + cofs;
+          for (int k = 0; k < 4; ++k) ob[k] = ((uint32_t)rl[k] * (uint32_t)src.ld2 + (uint32_t)cofs) * 4u;
         }
       };
       auto fetch = [&](int c, float (&o)[16]) {
         if (c == nc0) setsrc(ch.a0[1]);
         const int off = 64 * (c < nc0 ? c : c - nc0);
         if (ABL3(ABL_LOADS)) return;
-        ldfrag(pa, off, o);
+        ldfrag(ba, oa, off, o);
         if (gbr) {
           float t[16];
-          ldfrag(pb, off, t);
+          ldfrag(bb, ob, off, t);
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
         }
@@ -514,18 +524,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
       const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
       const bool has0 = (has_add0 || has_res) && !ABL3(ABL_LOADS), has1 = has_add1 && !ABL3(ABL_LOADS);
-      const float* p0[4];
-      const float* p1[4];
+      const float* b0 = nullptr;  // pf0 source
+      const float* b1 = nullptr;  // add[1] source, or the output rows
+      uint32_t o0[4], o1[4];
       float pf0[16], aux[16];
       {
         int rl[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
-        if (has0) row_ptrs(src0, bs, i0, rl, cofs, p0);
-        if (has1) row_ptrs(L.add[1], bs, i0, rl, cofs, p1);
+        if (has0) b0 = row_refs(src0, bs, i0, rl, cofs, o0);
+        if (has1) b1 = row_refs(L.add[1], bs, i0, rl, cofs, o1);
       }
-      if (has0) ldfrag(p0, 0, pf0);
-      if (has1) ldfrag(p1, 0, aux);
+      if (has0) ldfrag(b0, o0, 0, pf0);
+      if (has1) ldfrag(b1, o1, 0, aux);
       if (!waited) {
         tr.ev(600 + l);
         mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       }
       if (has_ln && !ABL3(ABL_LN)) {
         float pv[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll CHUNK_UNROLL
         for (int s = 0; s < 4; ++s) {
           float v[16];
           tmem_ld_16x256b_x2(taddr + 64 * s, v);
@@ -598,10 +609,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
       }
       if (has_out) {
+        b1 = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) p1[k] = L.out + ((size_t)bs * rows + i0 + rt[k]) * (size_t)L.ldo + cofs;
+        for (int k = 0; k < 4; ++k) o1[k] = ((uint32_t)rt[k] * (uint32_t)L.ldo + (uint32_t)cofs) * 4u;
       }
-#pragma unroll
+#pragma unroll CHUNK_UNROLL
       for (int s = 0; s < 4; ++s) {
         float v[16];
         if (!ABL3(ABL_TMEM)) {
@@ -648,16 +660,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           for (int i = 0; i < 16; ++i) v[i] += pf0[i];
         }
         if (s < 3) {  // next chunk's global operands: in flight while this chunk is stored / converted
-          if (has0) ldfrag(p0, 64 * (s + 1), pf0);
-          if (has1) ldfrag(p1, 64 * (s + 1), aux);
+          if (has0) ldfrag(b0, o0, 64 * (s + 1), pf0);
+          if (has1) ldfrag(b1, o1, 64 * (s + 1), aux);
         }
         if (has_out && !ABL3(ABL_STORES)) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (rt[k] < nvalid) {
               const int i = 8 * (k >> 1) + 2 * (k & 1);
-              float* o = const_cast<float*>(p1[k]);
-              *reinterpret_cast<float4*>(o + 64 * s) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+              char* o = reinterpret_cast<char*>(const_cast<float*>(b1) + 64 * s) + o1[k];
+              *reinterpret_cast<float4*>(o) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
             }
           }
         }
@@ -939,8 +951,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool simple_kind(int k) { return k == SRC_STREAM || k == SRC_BCAST || k == SRC_GATHER || k == SRC_BGATHER; }
 // a source every thread may read with 8-byte loads over `need` columns
+// byte offsets inside a fast-path source fit 32 bits: gathered rows are addressed relative to the sample, contiguous rows
+// relative to the tile
+static bool fits32(const RowSrc& s) {
+  const bool g = s.kind == SRC_GATHER || s.kind == SRC_BGATHER || s.kind == SRC_GATHER_BCAST_RELU;
+  const long long span = g ? (long long)s.src_rows : 128;
+  return span * (long long)s.ld * 4 + 4096 < (1ll << 32);
+}
 static bool src_fast(const RowSrc& s, int need) {
-  return simple_kind(s.kind) && s.width >= need && aligned16(s.base + s.col0) && !(s.ld & 3);
+  return simple_kind(s.kind) && s.width >= need && aligned16(s.base + s.col0) && !(s.ld & 3) && fits32(s);
 }
 
 cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
@@ -1002,7 +1021,7 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
       const RowSrc& s = ch.a0[a];
       if (s.kind == SRC_NONE) continue;
       const bool gbr = s.kind == SRC_GATHER_BCAST_RELU;
-      ok = ok && (simple_kind(s.kind) || gbr) && !(s.width & 63) && aligned16(s.base + s.col0) && !(s.ld & 3);
+      ok = ok && (simple_kind(s.kind) || gbr) && !(s.width & 63) && aligned16(s.base + s.col0) && !(s.ld & 3) && fits32(s);
       if (gbr) ok = ok && aligned16(s.base2) && !(s.ld2 & 3);
       wsum += s.width;
     }
@@ -1014,7 +1033,7 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     for (int a = 0; a < 2; ++a)
       if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], 256);
     if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, 256);
-    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= 256 && L.add[1].kind == SRC_NONE;
+    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= 256 && L.add[1].kind == SRC_NONE && L.ldo < (1 << 20);
     if (ok) ch.fast |= 1 << l;
   }
   if (getenv("GW_TC3_NOFAST")) ch.fast = 0;

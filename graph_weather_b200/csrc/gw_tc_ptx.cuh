@@ -84,7 +84,10 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
-struct Tracer {  // debug timeline of CTA 0 (one elected thread per role); a null buffer disables it
+// Debug timeline of CTA 0 (one elected thread per role).  Compiled in only for the diagnostics build (-DGW_ABLATE /
+// -DGW_TRACE, tools/ablate.py, tools/trace_chain.py): in the product build it costs no registers and no instructions.
+#if defined(GW_ABLATE) || defined(GW_TRACE)
+struct Tracer {
   long long* p;
   int n;
   __device__ __forceinline__ void init(long long* base, int role, bool on) { p = (base && on && blockIdx.x == 0) ? base + role * 2048 : nullptr, n = 0; }
@@ -96,6 +99,12 @@ struct Tracer {  // debug timeline of CTA 0 (one elected thread per role); a nul
     }
   }
 };
+#else
+struct Tracer {
+  __device__ __forceinline__ void init(long long*, int, bool) {}
+  __device__ __forceinline__ void ev(int) {}
+};
+#endif
 
 // tcgen05.ld 32 lanes x 32 columns of 32-bit: thread t of the warp receives TMEM lane (lane_base+t), columns c..c+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
