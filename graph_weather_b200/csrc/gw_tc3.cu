@@ -186,6 +186,10 @@ __device__ __forceinline__ void store_operand16(uint8_t* slot, const int (&rt)[4
 // and node passes: >95 % of the run time), a source is a warp-uniform 64-bit base plus four 32-bit byte offsets (one per row
 // of mine), resolved once per layer; every access is base + offset + immediate.  Contiguous sources are addressed relative
 // to the tile's first row, gathered ones relative to the sample (the launcher checks that this fits 32 bits).
+__device__ __forceinline__ const float* row_base(const RowSrc& s, int b, int i0) {
+  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
+  return src_gathered(s.kind) ? base : base + (size_t)i0 * (size_t)s.ld;
+}
 __device__ __forceinline__ const float* row_refs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, uint32_t (&off)[4]) {
   const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
   if (src_gathered(s.kind)) {
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       for (int c = 0; c < nk0; ++c) {
         if (c + 1 < nk0) fetch(c + 1, nxt);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
-        if (c >= A_SLOTS) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // operand wider than the ring
+        if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
         if (!ABL3(ABL_CONVERT)) store_operand16(smem + OFF_A + slot * A_SLOT_BYTES, rt, hq, lc, cur, split, amax);
         publish(slot);
         tr.ev(500 + c);
@@ -460,6 +464,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 
     // operand-store address of (my first row, chunk j = 0) inside a slot; see store_operand_fast
     const uint32_t sa0 = sbase + OFF_A + (32 * q + lr) * 128 + 4 * lc + (((2 * hq) ^ lr) << 4);
+
+    // gather offsets of layer 0's addends for the tile whose stage 0 ran last (resolved there, so that the index loads do
+    // not sit between two tiles)
+    uint32_t pre0[4], pre1[4];
+    const bool l0_add0 = ch.layer[0].add[0].kind != SRC_NONE, l0_add1 = ch.layer[0].add[1].kind != SRC_NONE;
 
     // ---- stage 0, lean path: every 64-column chunk lies inside one aligned source -----------------------------------------
     auto stage0_fast = [&](int tile) {
@@ -497,10 +506,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       float cur[16], nxt[16];
       setsrc(ch.a0[0]);
       fetch(0, cur);
+      if (l0_add0 && ((ch.fast >> 0) & 1)) (void)row_refs(ch.layer[0].add[0], bs, i0, rl, cofs, pre0);
+      if (l0_add1 && ((ch.fast >> 0) & 1)) (void)row_refs(ch.layer[0].add[1], bs, i0, rl, cofs, pre1);
       for (int c = 0; c < nk0; ++c) {
         if (c + 1 < nk0) fetch(c + 1, nxt);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
-        if (c >= A_SLOTS) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // operand wider than the ring
+        if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
         if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
         publish(slot);
         tr.ev(500 + c);
@@ -532,8 +543,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         int rl[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
-        if (has0) b0 = row_refs(src0, bs, i0, rl, cofs, o0);
-        if (has1) b1 = row_refs(L.add[1], bs, i0, rl, cofs, o1);
+        if (l == 0 && has_add0) {  // resolved during this tile's stage 0
+          b0 = row_base(src0, bs, i0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o0[k] = pre0[k];
+        } else if (has0) {
+          b0 = row_refs(src0, bs, i0, rl, cofs, o0);
+        }
+        if (l == 0 && has1) {
+          b1 = row_base(L.add[1], bs, i0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o1[k] = pre1[k];
+        } else if (has1) {
+          b1 = row_refs(L.add[1], bs, i0, rl, cofs, o1);
+        }
       }
       if (has0) ldfrag(b0, o0, 0, pf0);
       if (has1) ldfrag(b1, o1, 0, aux);
@@ -698,20 +721,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         const uint32_t acc = li & 1, use = li >> 1;
         const bool last_layer = l + 1 == n_layers;
         if (l < 0 || last_layer) {
-          if (l >= 0) {
-            // Every MMA of this tile has completed once this accumulator is full, so the whole operand ring is free:
-            // build the next tile's first operand now and let its first layer run on the other accumulator while this
-            // tile's last epilogue is computed.  (Before any per-layer state is live: the assembly needs the registers.)
-            tr.ev(600 + l);
-            mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
-            tc_fence_after();
-            tr.ev(610 + l);
-          }
+          // Stage 0 of the next tile is assembled here, before this tile's last epilogue: each operand slot is refilled as soon
+          // as the last layer's MMAs have read it (empty_a), so the assembly overlaps the tail of those MMAs and the next
+          // tile's first layer then runs on the other accumulator under this tile's last epilogue.  (Placed before any
+          // per-layer state is live: the assembly needs the registers.)
           const int t = l < 0 ? tile : next_tile;
           if (t < num_tiles) {
             if constexpr (FAST) stage0_fast(t); else stage0(t);
           }
           if (l < 0) continue;
+          tr.ev(600 + l);
+          mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+          tc_fence_after();
+          tr.ev(610 + l);
         }
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
