@@ -554,8 +554,16 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
       {
         TcChain ch;
         ch.rows_per_sample = N, ch.batch = cb;
-        ch.a0[0] = src_stream(f, d.in_dim, d.in_dim, N);
         ch.K0 = p->tc_enc_node.w0.K;
+        if (tc_generation() == 3 && ((d.in_dim & 63) || (reinterpret_cast<uintptr_t>(f) & 15))) {
+          // widen the feature rows to K0 (zero padded, 16-byte aligned) so that stage 0 takes the 128-bit path; the
+          // lat/lon row buffer is free here (the whole encoder block runs inside this chain)
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_pad_rows(f, d.in_dim, d.in_dim, xg, ch.K0, (long long)cb * N, st));
+          ch.a0[0] = src_stream(xg, ch.K0, ch.K0, N);
+        } else {
+          ch.a0[0] = src_stream(f, d.in_dim, d.in_dim, N);
+        }
         const Mlp &mn = p->enc_node, &me = p->enc_blk_edge;
         ch.layer[0] = tc_layer(p->tc_enc_node.w0, mn.b[0], true, true);
         ch.layer[1] = tc_layer(p->tc_enc_node.w1, mn.b[1], true, true);
@@ -790,6 +798,26 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
           ch.layer[2].feeds_next = 1;
           ch.layer[3] = tc_layer(p->tc_dec_out.w0, m.b[0], true, true);
           ch.layer[4] = tc_layer(p->tc_dec_out.w1, m.b[1], true, true);
+          if (tc_generation() == 3 && p->tc_dec_out.w1.N <= Dn && !(p->tc_dec_out.w1.N & 63)) {
+            // the narrow output layer (78 of 80 columns, 8-byte aligned rows) would take the whole chain off the lean
+            // path: run it as a chain of its own on the hidden rows h
+            ch.layer[4].feeds_next = 0;
+            const int Hd = p->tc_dec_out.w1.N;
+            tc_out(ch.layer[4], xg, Hd, Hd);
+            ch.n_layers = 5;
+            GW_TRY(run_chain(p, ch, st));
+            TcChain c2;
+            c2.rows_per_sample = No, c2.batch = cb;
+            c2.a0[0] = src_stream(xg, Hd, Hd, No);
+            c2.K0 = Hd;
+            c2.layer[0] = tc_layer(p->tc_dec_out.w2, m.b[2], false, false);
+            if (start && d.residual_dim > 0)
+              c2.layer[0].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
+            tc_out(c2.layer[0], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
+            c2.n_layers = 1;
+            GW_TRY(run_chain(p, c2, st));
+            continue;
+          }
           ch.layer[5] = tc_layer(p->tc_dec_out.w2, m.b[2], false, false);
           if (start && d.residual_dim > 0)
             ch.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);

@@ -14,6 +14,7 @@ void set_error(const std::string& msg);
 // exact-fp32 CUDA-core execution of one row op (gw_simt.cu)
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream);
 
+cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, cudaStream_t stream);
 cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows,
                           int rows, int batch, float* out, int ldo, cudaStream_t stream);
 

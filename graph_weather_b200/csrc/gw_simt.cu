@@ -194,6 +194,32 @@ cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* p
   return cudaGetLastError();
 }
 
+// dst[r, 0:ld_dst] = [src[r, 0:width], 0 ...]: widens rows whose width / stride are not multiples of 64 floats (the 102
+// input features) so that the tensor-core chain can read them with aligned 128-bit loads.
+__global__ void __launch_bounds__(256) gw_pad_rows_kernel(const float* __restrict__ src, int ld_src, int width, float* __restrict__ dst,
+                                                          int ld_dst, long long rows) {
+  const int q = ld_dst >> 2;  // float4 per destination row
+  const long long total = rows * q;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / q;
+    const int c = (int)(e - r * q) * 4;
+    const float* s = src + r * ld_src + c;
+    float4 v;
+    v.x = (c + 0 < width) ? __ldg(s + 0) : 0.f;
+    v.y = (c + 1 < width) ? __ldg(s + 1) : 0.f;
+    v.z = (c + 2 < width) ? __ldg(s + 2) : 0.f;
+    v.w = (c + 3 < width) ? __ldg(s + 3) : 0.f;
+    *reinterpret_cast<float4*>(dst + r * ld_dst + c) = v;
+  }
+}
+cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (ld_dst & 3) return cudaErrorInvalidValue;
+  gw_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>(src, ld_src, width, dst, ld_dst, rows);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream) {
   const long long R = (long long)op.rows_per_sample * op.batch;
   if (R <= 0 || op.N <= 0) return cudaSuccess;

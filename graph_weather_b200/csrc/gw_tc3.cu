@@ -240,7 +240,8 @@ __device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)
     }
 }
 
-template <bool SPLIT, bool FAST>
+// MODE 0: every part takes the general path; 1: every part takes the lean full-width path; 2: chosen per part (ch.fast)
+template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __grid_constant__ TcChain ch) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -521,12 +522,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       fi += nk0;
     };
 
-    // ---- one layer's epilogue, lean path: N = 256, full-width aligned addends / residual / output ------------------------
+    // ---- one layer's epilogue, lean path: N = 64 np (LayerNorm: N = 256), full-width aligned addends / residual / output ------------------------
     // Register budget: v[16] + pf0[16] + aux[16] + two row-pointer sets.  `aux` is the add[1] prefetch or, on LayerNorm layers
     // (which have no addends), the per-row scale/shift; `p1` is the add[1] rows or the output rows (never both: launcher).
     auto layer_fast = [&](int l, uint32_t acc, uint32_t use, bool waited, int bs, int i0, int nvalid, int ln_slot) {
       const TcLayer& L = ch.layer[l];
       const float wsi = L.wscale_inv;
+      const int np = L.N >> 6;
       const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
       const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
       const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         for (int k = 0; k < 4; ++k) o1[k] = ((uint32_t)rt[k] * (uint32_t)L.ldo + (uint32_t)cofs) * 4u;
       }
 #pragma unroll CHUNK_UNROLL
-      for (int s = 0; s < 4; ++s) {
+      for (int s = 0; s < np; ++s) {
         float v[16];
         if (!ABL3(ABL_TMEM)) {
           tmem_ld_16x256b_x2(taddr + 64 * s, v);
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
-        if (s == 3) {  // my last read of this accumulator
+        if (s + 1 == np) {  // my last read of this accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += pf0[i];
         }
-        if (s < 3) {  // next chunk's global operands: in flight while this chunk is stored / converted
+        if (s + 1 < np) {  // next chunk's global operands: in flight while this chunk is stored / converted
           if (has0) ldfrag(b0, o0, 64 * (s + 1), pf0);
           if (has1) ldfrag(b1, o1, 64 * (s + 1), aux);
         }
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         tr.ev(700 + 10 * l + s);
       }
-      if (feeds) fi += 4;
+      if (feeds) fi += np;
     };
 
     const int n_layers = ch.n_layers;
@@ -727,7 +729,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           // per-layer state is live: the assembly needs the registers.)
           const int t = l < 0 ? tile : next_tile;
           if (t < num_tiles) {
-            if constexpr (FAST) stage0_fast(t); else stage0(t);
+            if constexpr (MODE == 1) {
+              stage0_fast(t);
+            } else if constexpr (MODE == 0) {
+              stage0(t);
+            } else {
+              if (ch.fast < 0) stage0_fast(t); else stage0(t);
+            }
           }
           if (l < 0) continue;
           tr.ev(600 + l);
@@ -737,7 +745,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
-        if constexpr (FAST) {
+        if (MODE == 1 || (MODE == 2 && ((ch.fast >> l) & 1))) {
           layer_fast(l, acc, use, last_layer, bs, i0, nvalid, ln_slot);
           if (has_ln) ++ln_slot;
           ++li;
@@ -996,9 +1004,10 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     int n = 0;
     e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    const void* fns[4] = {(const void*)gw_chain_tc3_kernel<true, true>, (const void*)gw_chain_tc3_kernel<true, false>,
-                          (const void*)gw_chain_tc3_kernel<false, true>, (const void*)gw_chain_tc3_kernel<false, false>};
-    for (int i = 0; i < 4; ++i) {
+    const void* fns[6] = {(const void*)gw_chain_tc3_kernel<true, 0>,  (const void*)gw_chain_tc3_kernel<true, 1>,
+                          (const void*)gw_chain_tc3_kernel<true, 2>,  (const void*)gw_chain_tc3_kernel<false, 0>,
+                          (const void*)gw_chain_tc3_kernel<false, 1>, (const void*)gw_chain_tc3_kernel<false, 2>};
+    for (int i = 0; i < 6; ++i) {
       e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e != cudaSuccess) return e;
     }
@@ -1051,26 +1060,24 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   }
   for (int l = 0; l < ch.n_layers; ++l) {
     const TcLayer& L = ch.layer[l];
-    bool ok = L.N == 256 && L.n_valid == 256;
+    bool ok = (L.N == 256 || (L.N == 128 && !L.ln_g)) && L.n_valid == L.N;
     for (int a = 0; a < 2; ++a)
-      if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], 256);
-    if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, 256);
-    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= 256 && L.add[1].kind == SRC_NONE && L.ldo < (1 << 20);
+      if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], L.N);
+    if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, L.N);
+    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= L.N && L.add[1].kind == SRC_NONE && L.ldo < (1 << 20);
     if (ok) ch.fast |= 1 << l;
   }
   if (getenv("GW_TC3_NOFAST")) ch.fast = 0;
-  const bool all_fast = ch.fast == (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
+  const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
+  // (mode 2, per-part selection inside one kernel, measured slower than the general path: both paths' live state spills)
+  const int mode = ch.fast == all ? 1 : 0;
+#define GW_LAUNCH3(SPLIT_, MODE_) gw_chain_tc3_kernel<SPLIT_, MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch)
   if (ch.split) {
-    if (all_fast)
-      gw_chain_tc3_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
-    else
-      gw_chain_tc3_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+    if (mode == 1) GW_LAUNCH3(true, 1); else if (mode == 0) GW_LAUNCH3(true, 0); else GW_LAUNCH3(true, 2);
   } else {
-    if (all_fast)
-      gw_chain_tc3_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
-    else
-      gw_chain_tc3_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch);
+    if (mode == 1) GW_LAUNCH3(false, 1); else if (mode == 0) GW_LAUNCH3(false, 0); else GW_LAUNCH3(false, 2);
   }
+#undef GW_LAUNCH3
   count_launch();
   return cudaGetLastError();
 }
