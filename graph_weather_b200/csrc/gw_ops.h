@@ -71,6 +71,7 @@ struct TcLayer {
   int32_t ldo = 0, out_cols = 0;
   int32_t feeds_next = 0;     // result becomes the A operand of the next layer
   int32_t reuse_a = 0;        // this layer multiplies the same A operand as the previous layer
+  int32_t kind = -1;          // gw_tc3 launcher: epilogue feature mask if a specialised instance exists, else -1 (flags read at run time)
 };
 
 struct TcChain {

@@ -34,6 +34,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gw_internal.h"
 #include "gw_ops.h"
 #include "gw_tc_ptx.cuh"
@@ -48,6 +50,8 @@ namespace t3 {
 #endif
 enum { ABL_FENCE = 1, ABL_LOADS = 2, ABL_CONVERT = 4, ABL_STORES = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
 
+// epilogue feature mask of a layer (TcLayer::kind); the lean path is instantiated for the masks that occur
+enum { F_ADD0 = 1, F_ADD1 = 2, F_RELU = 4, F_LN = 8, F_RES = 16, F_OUT = 32, F_FEEDS = 64 };
 #ifndef GW_CHUNK_UNROLL
 #define GW_CHUNK_UNROLL 1  // the per-chunk loops stay rolled: unrolled, their code no longer fits the instruction cache
 #endif
@@ -525,14 +529,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     // ---- one layer's epilogue, lean path: N = 64 np (LayerNorm: N = 256), full-width aligned addends / residual / output ------------------------
     // Register budget: v[16] + pf0[16] + aux[16] + two row-pointer sets.  `aux` is the add[1] prefetch or, on LayerNorm layers
     // (which have no addends), the per-row scale/shift; `p1` is the add[1] rows or the output rows (never both: launcher).
-    auto layer_fast = [&](int l, uint32_t acc, uint32_t use, bool waited, int bs, int i0, int nvalid, int ln_slot) {
+    auto layer_fast = [&](auto FLc, int l, uint32_t acc, uint32_t use, bool waited, int bs, int i0, int nvalid, int ln_slot) {
+      constexpr int F = decltype(FLc)::value;  // >= 0: the layer's feature mask is a compile-time constant
       const TcLayer& L = ch.layer[l];
       const float wsi = L.wscale_inv;
       const int np = L.N >> 6;
       const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
-      const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
-      const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
-      const bool relu = L.relu != 0, has_ln = L.ln_g != nullptr, feeds = L.feeds_next != 0;
+      const bool has_add0 = F >= 0 ? (F & F_ADD0) != 0 : L.add[0].kind != SRC_NONE;
+      const bool has_add1 = F >= 0 ? (F & F_ADD1) != 0 : L.add[1].kind != SRC_NONE;
+      const bool has_res = F >= 0 ? (F & F_RES) != 0 : L.residual.kind != SRC_NONE;
+      const bool has_out = F >= 0 ? (F & F_OUT) != 0 : L.out != nullptr;
+      const bool relu = F >= 0 ? (F & F_RELU) != 0 : L.relu != 0;
+      const bool has_ln = F >= 0 ? (F & F_LN) != 0 : L.ln_g != nullptr;
+      const bool feeds = F >= 0 ? (F & F_FEEDS) != 0 : L.feeds_next != 0;
       const uint32_t g_o = OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_o = g_o + 1024;
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
       const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
@@ -746,7 +755,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
         if (MODE == 1 || (MODE == 2 && ((ch.fast >> l) & 1))) {
-          layer_fast(l, acc, use, last_layer, bs, i0, nvalid, ln_slot);
+#define GW_LF(M) case (M): layer_fast(std::integral_constant<int, (M)>{}, l, acc, use, last_layer, bs, i0, nvalid, ln_slot); break
+          switch (L.kind) {
+            GW_LF(F_ADD0 | F_ADD1 | F_RELU | F_FEEDS);  // edge layer 1: gathered P[src] + P[dst]
+            GW_LF(F_ADD0 | F_RELU | F_FEEDS);           // encoder edge layer 1: broadcast constant term
+            GW_LF(F_RELU | F_FEEDS);                    // hidden layers
+            GW_LF(F_LN | F_RES | F_OUT);                // last layer of an edge / node MLP
+            GW_LF(F_LN | F_FEEDS);                      // LayerNorm feeding the next MLP of the same chain
+            GW_LF(F_OUT);                               // per-node products P = x W^T
+            GW_LF(F_RELU | F_OUT);
+            default: layer_fast(std::integral_constant<int, -1>{}, l, acc, use, last_layer, bs, i0, nvalid, ln_slot); break;
+          }
+#undef GW_LF
           if (has_ln) ++ln_slot;
           ++li;
           tr.ev(900 + l);
@@ -1066,6 +1086,13 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, L.N);
     if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= L.N && L.add[1].kind == SRC_NONE && L.ldo < (1 << 20);
     if (ok) ch.fast |= 1 << l;
+    const int f = (L.add[0].kind != SRC_NONE ? F_ADD0 : 0) | (L.add[1].kind != SRC_NONE ? F_ADD1 : 0) | (L.relu ? F_RELU : 0) |
+                  (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0);
+    static const int kinds[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,
+                                F_LN | F_FEEDS, F_OUT, F_RELU | F_OUT};
+    ch.layer[l].kind = -1;
+    for (int k : kinds)
+      if (k == f) ch.layer[l].kind = f;
   }
   if (getenv("GW_TC3_NOFAST")) ch.fast = 0;
   const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
