@@ -222,10 +222,6 @@ static int run_op(gw_plan* p, const GemmOp& op, cudaStream_t st) {
   return 0;
 }
 
-int tc_generation() {
-  static const int gen = getenv("GW_TC_KERNEL") ? atoi(getenv("GW_TC_KERNEL")) : 3;
-  return gen == 2 ? 2 : 3;
-}
 static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   ch.split = (p->d.precision == GW_PREC_FP32_TC) ? 1 : 0;
   ch.status = p->tc_status_dev;
@@ -242,7 +238,7 @@ static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
   cudaError_t e;
   {
     TimedLaunch t(p, st);
-    e = tc_generation() == 2 ? launch_chain_tc(ch, st) : launch_chain_tc3(ch, st);
+    e = launch_chain_tc3(ch, st);
   }
   if (e != cudaSuccess) {
     set_error(std::string("tensor-core chain launch failed: ") + cudaGetErrorString(e));
@@ -452,7 +448,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
       scale = std::ldexp(1.f, 12 - e);   // amax * scale in [2048, 4096)
     }
     void* dst = p->tc_packed.p + off;
-    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, tc_generation() == 3 ? 1 : 0, dst, st));
+    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, 1, dst, st));
     reqs[i].out->p = dst;
     reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
     reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
@@ -555,7 +551,7 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
         TcChain ch;
         ch.rows_per_sample = N, ch.batch = cb;
         ch.K0 = p->tc_enc_node.w0.K;
-        if (tc_generation() == 3 && ((d.in_dim & 63) || (reinterpret_cast<uintptr_t>(f) & 15))) {
+        if ((d.in_dim & 63) || (reinterpret_cast<uintptr_t>(f) & 15)) {
           // widen the feature rows to K0 (zero padded, 16-byte aligned) so that stage 0 takes the 128-bit path; the
           // lat/lon row buffer is free here (the whole encoder block runs inside this chain)
           TimedLaunch t(p, st);
@@ -798,7 +794,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
           ch.layer[2].feeds_next = 1;
           ch.layer[3] = tc_layer(p->tc_dec_out.w0, m.b[0], true, true);
           ch.layer[4] = tc_layer(p->tc_dec_out.w1, m.b[1], true, true);
-          if (tc_generation() == 3 && p->tc_dec_out.w1.N <= Dn && !(p->tc_dec_out.w1.N & 63)) {
+          if (p->tc_dec_out.w1.N <= Dn && !(p->tc_dec_out.w1.N & 63)) {
             // the narrow output layer (78 of 80 columns, 8-byte aligned rows) would take the whole chain off the lean
             // path: run it as a chain of its own on the hidden rows h
             ch.layer[4].feeds_next = 0;

@@ -18,15 +18,13 @@ cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst,
 cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows,
                           int rows, int batch, float* out, int ldo, cudaStream_t stream);
 
-// tcgen05 chain kernel (gw_tc.cu)
-cudaError_t launch_chain_tc(const TcChain& ch, cudaStream_t stream);   // gw_tc.cu: mover/staging generation (GW_TC_KERNEL=2)
-cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream);  // gw_tc3.cu: direct fragment-layout generation (default)
+// tcgen05 chain kernel (gw_tc3.cu)
+cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream);
 // Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with
 // cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts).
 size_t tc_packed_bytes(int K_src, int N_src, int parts);
 cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm16, void* dst,
-                                cudaStream_t stream);  // perm16: feature order of gw_tc3.cu (see gw_pack_weights_kernel)
-int tc_generation();  // 3 (default): gw_tc3.cu, 2: gw_tc.cu  (GW_TC_KERNEL)
+                                cudaStream_t stream);  // perm16: feature order of gw_tc3.cu (gw_pack.cu)
 cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream);
 
 }  // namespace gw

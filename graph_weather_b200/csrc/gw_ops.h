@@ -51,13 +51,13 @@ struct GemmOp {
   int32_t ldo = 0;
 };
 
-// ---- tensor-core chain (gw_tc.cu) --------------------------------------------------------------------------------
+// ---- tensor-core chain (gw_tc3.cu) -------------------------------------------------------------------------------
 // A chain runs up to TC_MAX_LAYERS row ops back to back on one 128-row tile without leaving the SM: the result of a
 // layer is split to fp16 hi/lo and written straight into the shared-memory A operand of the next layer.
 constexpr int TC_MAX_LAYERS = 8;
 
 struct TcLayer {
-  const void* Wp = nullptr;   // packed weights (see pack kernel in gw_tc.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major
+  const void* Wp = nullptr;   // packed weights (gw_pack.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major
   int32_t K = 0, N = 0;       // K multiple of 64 (zero padded), N multiple of 16 (<= 256)
   int32_t n_valid = 0;        // real output columns (<= N); bias / LN parameters / addends exist only for these
   float wscale_inv = 1.f;     // weights are stored times a power of two; the accumulator is multiplied by this

@@ -12,8 +12,8 @@
 // product is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.  Weights are pre-scaled by a power of two so their lo
 // parts stay normal; the scale is undone exactly in the epilogue.
 //
-// Layout of the work (this is the third generation; gw_tc.cu's mover/staging design spent 40 % of its time in mbarrier
-// hand-offs, measured with tools/ablate.py):
+// Layout of the work (third generation; the second, with mover warps and shared-memory staging -- git history, profiles/r01_c_* --
+// spent 40 % of its time in mbarrier hand-offs, measured with tools/ablate.py):
 //   * 16 worker warps, four per TMEM lane quadrant.  A worker reads the accumulator with tcgen05.ld.16x256b, whose register
 //     fragment gives four adjacent lanes eight consecutive columns of one row (32 B = one sector).  In that fragment layout
 //     the workers load gathered addends / residual rows and store outputs DIRECTLY from/to global memory with 8-byte
@@ -95,7 +95,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // A worker thread's fragment of one 64-column chunk: 16 values, index i = 8g + 4j + 2m + e
 //   tile row  r(k) = 32 q + 16 g + lane/4 + 8 m   (k = 2g + m),   accumulator column = 16 hq + 8 j + 2 (lane%4) + e
-// The weights are packed with their output rows AND K columns permuted inside every group of 16 (perm16, gw_tc.cu) so that
+// The weights are packed with their output rows AND K columns permuted inside every group of 16 (perm16, gw_pack.cu) so that
 // accumulator column 8j + 2(lane%4) + e holds LOGICAL feature 4 (lane%4) + 2j + e: a thread owns 4 consecutive features of a row
 // (16 bytes of fp32) -> global loads / stores are 128-bit, four adjacent lanes cover 64 B of one row.  Operands live in shared
 // memory in accumulator order on both sides of every product, so nothing else changes.

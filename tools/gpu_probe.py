@@ -64,10 +64,10 @@ if __name__ == "__main__":
             if isinstance(o, _capi.Plan) and o.handle.value:
                 w = o.debug_words()
                 if w[0]:
-                    names = ["full_a0", "full_a1", "empty_a0", "empty_a1", "full_b0", "full_b1", "empty_b0", "empty_b1", "full_d0", "full_d1", "empty_d0", "empty_d1"] + [f"st_ready{i}" for i in range(5)] + [f"st_done{i}" for i in range(5)]
+                    names = [f"full_a{i}" for i in range(4)] + [f"empty_a{i}" for i in range(4)] + ["full_b0", "full_b1", "empty_b0", "empty_b1", "full_d0", "full_d1", "empty_d0", "empty_d1"]
                     print("status", w[0])
-                    for k in range(16):
+                    for k in range(20):
                         off, par, blk = w[4 + 3 * k : 7 + 3 * k]
                         if off:
-                            print(f"  warp {k:2d}: waiting {names[(off - 212992) // 8] if 0 <= (off - 212992) // 8 < len(names) else off} parity {par} block {blk}")
+                            print(f"  warp {k:2d}: waiting {names[(off - 196608) // 8] if 0 <= (off - 196608) // 8 < len(names) else off} parity {par} block {blk}")
         raise SystemExit(1)
