@@ -639,6 +639,7 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
   float* xb[2] = {p->xbuf0.p, p->xbuf1.p};
   float* eb[2] = {p->ebuf0.p, p->ebuf1.p};
   const float* e_cur = nullptr;  // null: block 0 reads e0
+  bool p_ready = false;          // P of the coming block was produced by the previous block's node chain
   for (int k = 0; k < d.num_blocks; ++k) {
     const Mlp& me = p->proc_edge[k];
     const Mlp& mn = p->proc_node[k];
@@ -648,15 +649,18 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
       if (x_next == x_cur) x_next = xb[(k & 1) ^ 1];
       const RowSrc e_src = e_cur ? src_stream(e_cur, De, De, El)
                                  : (g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El));
-      p->cur_tag = TAG_PROC_P;
-      for (int half = 0; half < 2; ++half) {  // P = x [W1s ; W1d]^T : one weight panel per launch
+      if (!p_ready) {  // P = x [W1s ; W1d]^T : two products of the same operand (block 0; later blocks: see the node chain)
+        p->cur_tag = TAG_PROC_P;
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
         ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
         ch.K0 = Dn;
-        ch.layer[0] = tc_layer(half ? p->tc_proc_edge[k].w0b : p->tc_proc_edge[k].w0, nullptr, false, false);
-        tc_out(ch.layer[0], p->P.p + half * He, 2 * He, He);
-        ch.n_layers = 1;
+        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0, nullptr, false, false);
+        tc_out(ch.layer[0], p->P.p, 2 * He, He);
+        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w0b, nullptr, false, false);
+        ch.layer[1].reuse_a = 1;
+        tc_out(ch.layer[1], p->P.p + He, 2 * He, He);
+        ch.n_layers = 2;
         GW_TRY(run_chain(p, ch, st));
       }
       p->cur_tag = TAG_PROC_EDGE;
@@ -680,7 +684,7 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
         {  // per-node sum of incoming e' rows (contiguous CSR segments of <= 7 rows): coalesced reduction kernel, so the
-           // chain stages two plain row streams
+           // chain reads two plain row streams
           TimedLaunch t(p, st);
           GW_CUDA(launch_segsum(e_next, De, De, g.ptr, nullptr, El, H, nb, p->agg_mesh.p, De, st));
         }
@@ -693,6 +697,19 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
         tc_ln(ch.layer[2], mn, src_stream(x_cur, Dn, Dn, H));
         tc_out(ch.layer[2], x_next, Dn, Dn);
         ch.n_layers = 3;
+        p_ready = false;
+        if (k + 1 < d.num_blocks && He == Dn) {
+          // the next block's P = x' [W1s ; W1d]^T needs exactly the rows this chain has just produced: two more products
+          // of the same operand, and the separate P launches (and their re-read of x') disappear
+          ch.layer[2].feeds_next = 1;
+          ch.layer[3] = tc_layer(p->tc_proc_edge[k + 1].w0, nullptr, false, false);
+          tc_out(ch.layer[3], p->P.p, 2 * He, He);
+          ch.layer[4] = tc_layer(p->tc_proc_edge[k + 1].w0b, nullptr, false, false);
+          ch.layer[4].reuse_a = 1;
+          tc_out(ch.layer[4], p->P.p + He, 2 * He, He);
+          ch.n_layers = 5;
+          p_ready = true;
+        }
         GW_TRY(run_chain(p, ch, st));
       }
       x_cur = x_next;

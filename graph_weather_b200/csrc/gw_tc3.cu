@@ -244,7 +244,8 @@ __device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)
     }
 }
 
-// MODE 0: every part takes the general path; 1: every part takes the lean full-width path; 2: chosen per part (ch.fast)
+// MODE 0: every part takes the general path; 1: every part takes the lean full-width path.  (A third mode that chose per
+// part inside one kernel was measured slower than the general path: the live state of both paths spills.)
 template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __grid_constant__ TcChain ch) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -740,10 +741,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           if (t < num_tiles) {
             if constexpr (MODE == 1) {
               stage0_fast(t);
-            } else if constexpr (MODE == 0) {
-              stage0(t);
             } else {
-              if (ch.fast < 0) stage0_fast(t); else stage0(t);
+              stage0(t);
             }
           }
           if (l < 0) continue;
@@ -754,13 +753,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
-        if (MODE == 1 || (MODE == 2 && ((ch.fast >> l) & 1))) {
+        if constexpr (MODE == 1) {
 #define GW_LF(M) case (M): layer_fast(std::integral_constant<int, (M)>{}, l, acc, use, last_layer, bs, i0, nvalid, ln_slot); break
           switch (L.kind) {
             GW_LF(F_ADD0 | F_ADD1 | F_RELU | F_FEEDS);  // edge layer 1: gathered P[src] + P[dst]
             GW_LF(F_ADD0 | F_RELU | F_FEEDS);           // encoder edge layer 1: broadcast constant term
             GW_LF(F_RELU | F_FEEDS);                    // hidden layers
             GW_LF(F_LN | F_RES | F_OUT);                // last layer of an edge / node MLP
+            GW_LF(F_LN | F_RES | F_OUT | F_FEEDS);      // ... whose rows are also the operand of the next block's P products
             GW_LF(F_LN | F_FEEDS);                      // LayerNorm feeding the next MLP of the same chain
             GW_LF(F_OUT);                               // per-node products P = x W^T
             GW_LF(F_RELU | F_OUT);
@@ -1012,57 +1012,9 @@ static bool src_fast(const RowSrc& s, int need) {
   return simple_kind(s.kind) && s.width >= need && aligned16(s.base + s.col0) && !(s.ld & 3) && fits32(s);
 }
 
-cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
-  TcChain ch = ch_in;
+// Marks which parts of a chain take the lean full-width path (ch.fast) and the epilogue kind of every layer.
+static void tc3_mark_lean(TcChain& ch) {
   using namespace t3;
-  static int num_sms[64] = {0};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (num_sms[dev] == 0) {
-    int n = 0;
-    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    const void* fns[6] = {(const void*)gw_chain_tc3_kernel<true, 0>,  (const void*)gw_chain_tc3_kernel<true, 1>,
-                          (const void*)gw_chain_tc3_kernel<true, 2>,  (const void*)gw_chain_tc3_kernel<false, 0>,
-                          (const void*)gw_chain_tc3_kernel<false, 1>, (const void*)gw_chain_tc3_kernel<false, 2>};
-    for (int i = 0; i < 6; ++i) {
-      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-    }
-    num_sms[dev] = n;
-  }
-  const long long R = (long long)ch.rows_per_sample * ch.batch;
-  if (R <= 0 || ch.n_layers <= 0) return cudaSuccess;
-  // structural requirements of the kernel
-  if (ch.n_layers > PAR_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
-  int n_ln = 0;
-  if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 63)) return cudaErrorInvalidValue;  // a chunk never straddles two sources
-  if (ch.layer[ch.n_layers - 1].feeds_next) return cudaErrorInvalidValue;
-  for (int a = 0; a < 2; ++a)
-    if (ch.a0[a].kind == SRC_SEGSUM) return cudaErrorInvalidValue;  // reduce with gw_segsum_kernel first
-  for (int l = 0; l < ch.n_layers; ++l) {
-    const TcLayer& L = ch.layer[l];
-    if (!L.Wp || (L.K & 63) || (L.N & 15) || L.N > 256 || L.N <= 0 || L.n_valid <= 0 || L.n_valid > L.N) return cudaErrorInvalidValue;
-    if (L.feeds_next && (L.N & 63)) return cudaErrorInvalidValue;
-    if (L.ln_g && L.add[0].kind != SRC_NONE) return cudaErrorInvalidValue;  // addends are applied before ReLU, not before LayerNorm
-    if (L.ln_g && (L.n_valid != L.N || ++n_ln > 2)) return cudaErrorInvalidValue;
-    if (L.add[0].kind == SRC_NONE && L.add[1].kind != SRC_NONE) return cudaErrorInvalidValue;
-    for (int a = 0; a < 2; ++a)
-      if (L.add[a].kind != SRC_NONE && L.add[a].kind != SRC_STREAM && L.add[a].kind != SRC_BCAST && L.add[a].kind != SRC_GATHER &&
-          L.add[a].kind != SRC_BGATHER)
-        return cudaErrorInvalidValue;
-    if (L.residual.kind != SRC_NONE && L.residual.kind != SRC_STREAM && L.residual.kind != SRC_BCAST && L.residual.kind != SRC_GATHER &&
-        L.residual.kind != SRC_BGATHER)
-      return cudaErrorInvalidValue;
-    if (L.add[0].kind != SRC_NONE && L.residual.kind != SRC_NONE) return cudaErrorInvalidValue;  // they share the prefetch registers
-    if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
-    if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;
-    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next || L.K > 64 * A_SLOTS)) return cudaErrorInvalidValue;  // the whole operand must still be resident
-  }
-  const int tiles = ((ch.rows_per_sample + TILE_M - 1) / TILE_M) * ch.batch;
-  const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
   // which parts take the lean full-width path
   ch.fast = 0;
   {
@@ -1089,20 +1041,74 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     const int f = (L.add[0].kind != SRC_NONE ? F_ADD0 : 0) | (L.add[1].kind != SRC_NONE ? F_ADD1 : 0) | (L.relu ? F_RELU : 0) |
                   (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0);
     static const int kinds[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,
-                                F_LN | F_FEEDS, F_OUT, F_RELU | F_OUT};
+                                F_LN | F_FEEDS, F_OUT, F_RELU | F_OUT, F_LN | F_RES | F_OUT | F_FEEDS};
     ch.layer[l].kind = -1;
     for (int k : kinds)
       if (k == f) ch.layer[l].kind = f;
   }
+}
+cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
+  TcChain ch = ch_in;
+  using namespace t3;
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (num_sms[dev] == 0) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    const void* fns[4] = {(const void*)gw_chain_tc3_kernel<true, 0>, (const void*)gw_chain_tc3_kernel<true, 1>,
+                          (const void*)gw_chain_tc3_kernel<false, 0>, (const void*)gw_chain_tc3_kernel<false, 1>};
+    for (int i = 0; i < 4; ++i) {
+      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+    }
+    num_sms[dev] = n;
+  }
+  const long long R = (long long)ch.rows_per_sample * ch.batch;
+  if (R <= 0 || ch.n_layers <= 0) return cudaSuccess;
+  // structural requirements of the kernel
+  if (ch.n_layers > PAR_LAYERS || ch.K0 <= 0 || (ch.K0 & 63)) return cudaErrorInvalidValue;
+  int n_ln = 0;
+  if (ch.a0[1].kind != SRC_NONE && (ch.a0[0].width & 63)) return cudaErrorInvalidValue;  // a chunk never straddles two sources
+  if (ch.layer[ch.n_layers - 1].feeds_next) return cudaErrorInvalidValue;
+
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const TcLayer& L = ch.layer[l];
+    if (!L.Wp || (L.K & 63) || (L.N & 15) || L.N > 256 || L.N <= 0 || L.n_valid <= 0 || L.n_valid > L.N) return cudaErrorInvalidValue;
+    if (L.feeds_next && (L.N & 63)) return cudaErrorInvalidValue;
+    if (L.ln_g && L.add[0].kind != SRC_NONE) return cudaErrorInvalidValue;  // addends are applied before ReLU, not before LayerNorm
+    if (L.ln_g && (L.n_valid != L.N || ++n_ln > 2)) return cudaErrorInvalidValue;
+    if (L.add[0].kind == SRC_NONE && L.add[1].kind != SRC_NONE) return cudaErrorInvalidValue;
+    for (int a = 0; a < 2; ++a)
+      if (L.add[a].kind != SRC_NONE && L.add[a].kind != SRC_STREAM && L.add[a].kind != SRC_BCAST && L.add[a].kind != SRC_GATHER &&
+          L.add[a].kind != SRC_BGATHER)
+        return cudaErrorInvalidValue;
+    if (L.residual.kind != SRC_NONE && L.residual.kind != SRC_STREAM && L.residual.kind != SRC_BCAST && L.residual.kind != SRC_GATHER &&
+        L.residual.kind != SRC_BGATHER)
+      return cudaErrorInvalidValue;
+    if (L.add[0].kind != SRC_NONE && L.residual.kind != SRC_NONE) return cudaErrorInvalidValue;  // they share the prefetch registers
+    if (l == 0 && L.K != ch.K0) return cudaErrorInvalidValue;
+    if (l > 0 && !L.reuse_a && (!ch.layer[l - 1].feeds_next || ch.layer[l - 1].N != L.K)) return cudaErrorInvalidValue;
+    if (L.reuse_a && (l == 0 || L.K != ch.layer[l - 1].K || ch.layer[l - 1].feeds_next || L.K > 64 * A_SLOTS)) return cudaErrorInvalidValue;  // the whole operand must still be resident
+  }
+  const int tiles = ((ch.rows_per_sample + TILE_M - 1) / TILE_M) * ch.batch;
+  const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+  tc3_mark_lean(ch);
   if (getenv("GW_TC3_NOFAST")) ch.fast = 0;
   const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
   // (mode 2, per-part selection inside one kernel, measured slower than the general path: both paths' live state spills)
   const int mode = ch.fast == all ? 1 : 0;
+  for (int a = 0; a < 2; ++a)
+    if (ch.a0[a].kind == SRC_SEGSUM) return cudaErrorInvalidValue;  // reduce with gw_segsum_kernel first (a fused per-thread
+                                                                    // reduction in stage 0 was measured slower than the kernel)
 #define GW_LAUNCH3(SPLIT_, MODE_) gw_chain_tc3_kernel<SPLIT_, MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch)
   if (ch.split) {
-    if (mode == 1) GW_LAUNCH3(true, 1); else if (mode == 0) GW_LAUNCH3(true, 0); else GW_LAUNCH3(true, 2);
+    if (mode == 1) GW_LAUNCH3(true, 1); else GW_LAUNCH3(true, 0);
   } else {
-    if (mode == 1) GW_LAUNCH3(false, 1); else if (mode == 0) GW_LAUNCH3(false, 0); else GW_LAUNCH3(false, 2);
+    if (mode == 1) GW_LAUNCH3(false, 1); else GW_LAUNCH3(false, 0);
   }
 #undef GW_LAUNCH3
   count_launch();
