@@ -18,7 +18,7 @@ buf = m._engine.plan.trace_next(a.tag)
 m(x); torch.cuda.synchronize()
 t = buf.cpu().numpy()
 np.save(a.out, t)
-roles = ["producer", "mma", "mover0", "mover1", "mover2", "worker_h0", "worker_h1", "-"]
+roles = ["producer", "mma", "-", "-", "-", "worker_q0_h0", "worker_q0_h1", "-"]
 t0 = min(int(t[r, 0, 0]) for r in range(8) if t[r, 0, 0] > 0)
 for r in range(8):
     ev = [(int(c) - t0, int(k)) for c, k in t[r] if c > 0]
