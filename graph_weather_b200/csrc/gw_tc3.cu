@@ -75,7 +75,8 @@ constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_PAR = OFF_TMEM + 16;                // float bias[PAR_LAYERS][256]
 constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;  // float gamma_beta[2][2][256]
 constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_x[WSPLIT][128], ln_y[WSPLIT][128]: row statistics exchange
-constexpr int SMEM_BYTES = OFF_LN + 2 * WSPLIT * 128 * 4;
+constexpr int OFF_PRE = OFF_LN + 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather offsets of the coming tile
+constexpr int SMEM_BYTES = OFF_PRE + 8 * NUM_WORKERS * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
 
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 
     // gather offsets of layer 0's addends for the tile whose stage 0 ran last (resolved there, so that the index loads do
     // not sit between two tiles)
-    uint32_t pre0[4], pre1[4];
+    uint32_t* pre_s = reinterpret_cast<uint32_t*>(smem + OFF_PRE) + threadIdx.x;  // [8][NUM_WORKERS], one column per thread
     const bool l0_add0 = ch.layer[0].add[0].kind != SRC_NONE, l0_add1 = ch.layer[0].add[1].kind != SRC_NONE;
 
     // ---- stage 0, lean path: every 64-column chunk lies inside one aligned source -----------------------------------------
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const int nk0 = ch.K0 >> 6, nc0 = ch.a0[0].width >> 6;
       const float* ba = nullptr;
       const float* bb = nullptr;
-      uint32_t oa[4], ob[4];
+      uint32_t oa[4] = {0u, 0u, 0u, 0u}, ob[4] = {0u, 0u, 0u, 0u};  // (initialised: arrays assigned only on some paths end up in local memory)
       bool gbr = false;
       auto setsrc = [&](const RowSrc& src) {
         ba = row_refs(src, bs, i0, rl, cofs, oa);
@@ -512,8 +513,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       float cur[16], nxt[16];
       setsrc(ch.a0[0]);
       fetch(0, cur);
-      if (l0_add0 && ((ch.fast >> 0) & 1)) (void)row_refs(ch.layer[0].add[0], bs, i0, rl, cofs, pre0);
-      if (l0_add1 && ((ch.fast >> 0) & 1)) (void)row_refs(ch.layer[0].add[1], bs, i0, rl, cofs, pre1);
+      if (l0_add0) {  // kept in shared memory (one word per thread and row): registers are the scarce resource of the epilogues
+        uint32_t t[4];
+        (void)row_refs(ch.layer[0].add[0], bs, i0, rl, cofs, t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = t[k];
+      }
+      if (l0_add1) {
+        uint32_t t[4];
+        (void)row_refs(ch.layer[0].add[1], bs, i0, rl, cofs, t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = t[k];
+      }
       for (int c = 0; c < nk0; ++c) {
         if (c + 1 < nk0) fetch(c + 1, nxt);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const bool has0 = (has_add0 || has_res) && !ABL3(ABL_LOADS), has1 = has_add1 && !ABL3(ABL_LOADS);
       const float* b0 = nullptr;  // pf0 source
       const float* b1 = nullptr;  // add[1] source, or the output rows
-      uint32_t o0[4], o1[4];
+      uint32_t o0[4] = {0u, 0u, 0u, 0u}, o1[4] = {0u, 0u, 0u, 0u};  // (initialised: see stage0_fast)
       float pf0[16], aux[16];
       {
         int rl[4];
@@ -558,19 +569,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         if (l == 0 && has_add0) {  // resolved during this tile's stage 0
           b0 = row_base(src0, bs, i0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o0[k] = pre0[k];
+          for (int k = 0; k < 4; ++k) o0[k] = pre_s[k * NUM_WORKERS];
         } else if (has0) {
           b0 = row_refs(src0, bs, i0, rl, cofs, o0);
         }
         if (l == 0 && has1) {
           b1 = row_base(L.add[1], bs, i0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o1[k] = pre1[k];
+          for (int k = 0; k < 4; ++k) o1[k] = pre_s[(4 + k) * NUM_WORKERS];
         } else if (has1) {
           b1 = row_refs(L.add[1], bs, i0, rl, cofs, o1);
         }
       }
-      if (has0) ldfrag(b0, o0, 0, pf0);
+      if (has0 && !has_ln) ldfrag(b0, o0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
       if (has1) ldfrag(b1, o1, 0, aux);
       if (!waited) {
         tr.ev(600 + l);
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         for (int k = 0; k < 4; ++k) aux[k] = 1.f, aux[4 + k] = 0.f;
       }
       if (has_ln && !ABL3(ABL_LN)) {
-        float pv[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        float pv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll CHUNK_UNROLL
         for (int s = 0; s < 4; ++s) {
           float v[16];
@@ -605,6 +616,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             s2[k] = fmaf(d, d, s2[k]);
           }
         }
+        if (has0) ldfrag(b0, o0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
         float mean[4], m2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -643,6 +655,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
       }
+      if (has_ln && ABL3(ABL_LN) && has0) ldfrag(b0, o0, 0, pf0);
       if (has_out) {
         b1 = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo;
 #pragma unroll
@@ -809,7 +822,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         // the 4 lanes and 4 warps that share a row: one pass, no cancellation, one barrier.
         float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
         if (has_ln && !ABL3(ABL_LN)) {
-          float pv[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          float pv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
           int cnt = 0;
           for (int s = 0; s < np; ++s) {
             if (64 * s + 16 * hq >= N) break;
