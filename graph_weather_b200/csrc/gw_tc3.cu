@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
       for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
       const int nk0 = ch.K0 >> 6, w0 = ch.a0[0].width;
-      int ri[4], ri2[4];  // rows of the current source (and of its broadcast partner)
+      int ri[4] = {0, 0, 0, 0}, ri2[4] = {0, 0, 0, 0};  // rows of the current source (and of its broadcast partner)
       int cur_src = -1;
       auto fetch = [&](int c, float (&o)[16]) {
         const int colc = 64 * c;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const float* b0 = nullptr;  // pf0 source
       const float* b1 = nullptr;  // add[1] source, or the output rows
       uint32_t o0[4] = {0u, 0u, 0u, 0u}, o1[4] = {0u, 0u, 0u, 0u};  // (initialised: see stage0_fast)
-      float pf0[16], aux[16];
+      float pf0[16] = {}, aux[16] = {};
       {
         int rl[4];
 #pragma unroll
@@ -800,8 +800,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         //   pf0 = addend 0 (before the activation) or, on layers without addends, the residual (after LayerNorm); pf1 = addend 1
         const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
         const bool has0 = has_add0 || has_res;
-        int r0[4], r1[4];
-        float pf0[16], pf1[16];
+        int r0[4] = {0, 0, 0, 0}, r1[4] = {0, 0, 0, 0};
+        float pf0[16] = {}, pf1[16] = {};
         auto prefetch = [&](int s) {
           if (64 * s + 16 * hq >= N || ABL3(ABL_LOADS)) return;
           if (has0) load16(src0, bs, r0, 64 * s + cofs, lc, pf0);
