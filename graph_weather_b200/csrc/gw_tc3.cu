@@ -93,6 +93,15 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for TMEM loads that were issued earlier into v (asynchronously: the compiler believes v was written by the issuing
+// statement).  Passing v through the wait as in/out operands makes every later read of v depend on the wait.
+__device__ __forceinline__ void tmem_wait_ld_into(float (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                 "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
 
 // A worker thread's fragment of one 64-column chunk: 16 values, index i = 8g + 4j + 2m + e
 //   tile row  r(k) = 32 q + 16 g + lane/4 + 8 m   (k = 2g + m),   accumulator column = 16 hq + 8 j + 2 (lane%4) + e
@@ -661,16 +670,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
         for (int k = 0; k < 4; ++k) o1[k] = ((uint32_t)rt[k] * (uint32_t)L.ldo + (uint32_t)cofs) * 4u;
       }
+      // The accumulator chunk s+1 is fetched from TMEM (into vn) while chunk s is processed (in v).
+      float vn[16] = {};
+      if (!ABL3(ABL_TMEM)) {
+        tmem_ld_16x256b_x2(taddr, vn);
+        tmem_ld_16x256b_x2(taddr + (16u << 16), vn + 8);
+      }
 #pragma unroll CHUNK_UNROLL
       for (int s = 0; s < np; ++s) {
         float v[16];
-        if (!ABL3(ABL_TMEM)) {
-          tmem_ld_16x256b_x2(taddr + 64 * s, v);
-          tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
-          tmem_wait_ld();
-        } else {
+        tmem_wait_ld_into(vn);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        if (s + 1 < np && !ABL3(ABL_TMEM)) {
+          tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vn);
+          tmem_ld_16x256b_x2(taddr + 64 * (s + 1) + (16u << 16), vn + 8);
         }
         if (s + 1 == np) {  // my last read of this accumulator
           tc_fence_before();
