@@ -162,6 +162,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
 
+    # stdout carries exactly one JSON line: anything libraries print in between (NCCL's version banner comes from C code)
+    # is sent to stderr by pointing file descriptor 1 there until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,7 +189,7 @@ def main():
         sample_b = min(2, a.batch)
         sps, t, cores = time_cpu_reference(lat_lons, a.batch, sample_b, max(1, a.steps), max(0, a.warmup))
         sample = f"{sample_b} of the {a.batch} samples of a step per timed forward (1deg grid); steps/s = samples/s / {a.batch}"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "forward steps/sec", "value": sps, "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -332,7 +344,7 @@ def main():
         sps, t, cores = time_cpu_reference(lat_lons, a.batch, sample_b, 2, 1)
         line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "seconds_per_forward": t,
                                 "sample": f"oracle port of the reference forward, {sample_b} of the {a.batch} samples per forward, 1 warm-up + 2 timed; steps/s = samples/s / {a.batch}"}  # fmt: skip
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
