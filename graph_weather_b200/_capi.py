@@ -60,6 +60,8 @@ _SIGNATURES = {
     "gw_timing_num_tags": (_i32, []),
     "gw_timing_tag_name": (ctypes.c_char_p, [_i32]),
     "gw_timing_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double), _vp]),
+    "gw_loss_workspace_bytes": (_i64, []),
+    "gw_normalized_mse_loss_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "gw_launch_count": (_i64, []),
     "gw_launch_count_reset": (None, []),
 }

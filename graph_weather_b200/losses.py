@@ -1,0 +1,89 @@
+"""Loss boundary of the forward: a mirror of graph_weather/models/losses.py:9-94 (`NormalizedMSELoss`) whose reduction runs in
+one HBM-bound CUDA kernel behind the C ABI (`gw_normalized_mse_loss_sum`).  Forward only; there is no CPU
+fallback: tensors must live on a CUDA device.
+
+Data-parallel use: every rank reduces its own batch shard to one double and the ranks all-reduce that scalar
+(`forward(pred, target, group=...)`), instead of all-gathering the [B, N, F] outputs to evaluate the loss on every rank."""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def node_weights(lat_lons, num_nodes: int) -> np.ndarray:
+    """cos(latitude) of every grid node exactly as the reference tiles it (losses.py:37-42, 78-88): the sorted unique
+    latitudes, each repeated num_nodes // num_unique times in node order."""
+    unique_lats = sorted(set(lat for lat, _ in lat_lons))
+    w = np.array([np.cos(lat * np.pi / 180.0) for lat in unique_lats]).astype(np.float32)  # torch.tensor(..., dtype=float)
+    num_unique = w.shape[0]
+    num_lon = num_nodes // num_unique
+    if num_unique * num_lon != num_nodes:  # the reference's reshape(1, num_nodes) fails the same way (losses.py:84)
+        raise RuntimeError(f"shape '[1, {num_nodes}]' is invalid for input of size {num_unique * num_lon}")
+    return np.repeat(w, num_lon)
+
+
+class NormalizedMSELoss(torch.nn.Module):
+    """Variance-normalised, cos(lat)-weighted MSE (losses.py:9-94): same constructor, same `forward(pred, target)` value."""
+
+    def __init__(self, feature_variance: list, lat_lons: list, device="cpu", normalize: bool = False):
+        super().__init__()
+        self.feature_variance = torch.tensor(feature_variance)
+        assert not torch.isnan(self.feature_variance).any()
+        self.lat_lons = [(float(a), float(b)) for a, b in lat_lons]
+        unique_lats = sorted(set(lat for lat, _ in self.lat_lons))
+        self.weights = torch.tensor([np.cos(lat * np.pi / 180.0) for lat in unique_lats], dtype=torch.float)
+        self.normalize = normalize
+        assert not torch.isnan(self.weights).any()
+        self._dev = {}  # per device: (inv_variance, node_weight, workspace, sum)
+
+    def _device_state(self, device, num_nodes):
+        key = (str(device), num_nodes)
+        if key not in self._dev:
+            lib = _capi.load()
+            inv = (1.0 / self.feature_variance.to(torch.float32)).to(device).contiguous()
+            w = torch.from_numpy(node_weights(self.lat_lons, num_nodes)).to(device)
+            ws = torch.empty(int(lib.gw_loss_workspace_bytes()), dtype=torch.uint8, device=device)
+            s = torch.zeros(1, dtype=torch.float64, device=device)
+            self._dev[key] = (inv, w, ws, s)
+        return self._dev[key]
+
+    def local_sum(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """sum over the local rows of w(n) * mean_f(...): a 1-element float64 device tensor (valid until the next call)."""
+        if not (pred.is_cuda and target.is_cuda):
+            raise RuntimeError("graph_weather_b200.NormalizedMSELoss runs on CUDA tensors only (no CPU fallback)")
+        if pred.shape != target.shape:
+            raise RuntimeError(f"pred {tuple(pred.shape)} and target {tuple(target.shape)} differ")
+        lib = _capi.load()
+        F = pred.shape[-1]
+        B = pred.shape[0]
+        num_nodes = int(np.prod(pred.shape[1:-1]))
+        if self.normalize and self.feature_variance.numel() != F:
+            raise RuntimeError("feature_variance does not match the feature dimension")
+        p = pred.detach().to(torch.float32).contiguous()
+        t = target.detach().to(torch.float32).contiguous()
+        inv, w, ws, s = self._device_state(pred.device, num_nodes)
+        with torch.cuda.device(pred.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _capi._check(lib.gw_normalized_mse_loss_sum(
+                ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(t.data_ptr()),
+                ctypes.c_void_p(inv.data_ptr()) if self.normalize else None, ctypes.c_void_p(w.data_ptr()), B, num_nodes, F,
+                ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(st)))  # fmt: skip
+        return s
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor, group=None, total_batch: int | None = None):
+        """losses.py:46-94.  With `group` (torch.distributed), `pred` / `target` are this rank's batch shard and the result is
+        the loss over the whole batch of `total_batch` samples: the ranks exchange one scalar."""
+        s = self.local_sum(pred, target)
+        rows = pred.shape[0] * int(np.prod(pred.shape[1:-1]))
+        if group is not None or total_batch is not None:
+            import torch.distributed as dist
+
+            s = s.clone()
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+            rows = int(total_batch) * int(np.prod(pred.shape[1:-1]))
+        return (s / rows).to(torch.float32).reshape(())

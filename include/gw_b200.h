@@ -140,6 +140,17 @@ int32_t gw_timing_num_tags(void);
 const char* gw_timing_tag_name(int32_t tag);
 int gw_timing_read(gw_plan* plan, int64_t* launches, double* milliseconds, void* stream);
 
+/* Loss boundary (forward): NormalizedMSELoss.forward, graph_weather/models/losses.py:46-94.
+ *   *sum_out = sum over b < batch, n < n_nodes of  node_weight[n] * mean_f( (pred - target)^2 * inv_variance[f] )
+ * pred / target: [batch, n_nodes, n_features] fp32 row-major device pointers; inv_variance: [n_features] (1 / feature_variance,
+ * losses.py:70) or NULL when the reference's `normalize` is False; node_weight: [n_nodes] = cos(latitude) tiled as
+ * losses.py:83-88.  The reference's value is *sum_out / (batch * n_nodes) (losses.py:94); data-parallel ranks add their sums
+ * (one all-reduced scalar) and divide by the global row count.  workspace: gw_loss_workspace_bytes() device bytes.
+ * Deterministic (fixed reduction tree), independent of any plan. */
+int64_t gw_loss_workspace_bytes(void);
+int gw_normalized_mse_loss_sum(const float* pred, const float* target, const float* inv_variance, const float* node_weight,
+                               int64_t batch, int64_t n_nodes, int32_t n_features, double* sum_out, void* workspace, void* stream);
+
 /* Counters for bench.py: kernels launched by this library on the calling thread since the last reset. */
 int64_t gw_launch_count(void);
 void gw_launch_count_reset(void);

@@ -92,6 +92,23 @@ def _install_third_party_shims():
         sys.modules["h3"] = h3lite
 
 
+def load_reference_losses():
+    """graph_weather/models/losses.py imported unmodified; its top-level `import torch_harmonics` (used only by the spectral
+    AMSE loss, not by NormalizedMSELoss) is satisfied by a stub module."""
+    if not available():
+        raise RuntimeError(f"reference sources not found under {REFERENCE_ROOT} (only present in the build container)")
+    import importlib.util
+
+    if "torch_harmonics" not in sys.modules:
+        th = types.ModuleType("torch_harmonics")
+        th.RealSHT = type("RealSHT", (), {})  # only named in a type annotation of the AMSE loss (losses.py:132)
+        sys.modules["torch_harmonics"] = th
+    spec = importlib.util.spec_from_file_location("_gw_reference_losses", os.path.join(REFERENCE_ROOT, "graph_weather", "models", "losses.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 _loaded = None
 
 

@@ -230,3 +230,22 @@ def build_assimilator_graphs(output_lat_lons, resolution=2):
         base_h3_grid=base, lat_edge_index=lat_ei, lat_edge_attr=lat_ea, dec_edge_index=dec_ei, dec_edge_attr=dec_ea,
         num_latlons=len(output_lat_lons), num_h3=num_h3,
     )  # fmt: skip
+
+
+def normalized_mse_loss(pred, target, feature_variance, lat_lons, normalize=False):
+    """NormalizedMSELoss.forward restated op for op (graph_weather/models/losses.py:37-42, 60-94): squared error, optional
+    division by the feature variance, mean over features, cos(lat) weights tiled per unique latitude, mean over batch x nodes."""
+    fv = torch.tensor(feature_variance)
+    unique_lats = sorted(set(lat for lat, _ in lat_lons))  # losses.py:38
+    weights = torch.tensor([np.cos(lat * np.pi / 180.0) for lat in unique_lats], dtype=torch.float)  # losses.py:40-42
+    out = (pred - target) ** 2  # losses.py:66
+    if normalize:
+        out = out / fv  # losses.py:69-70
+    out = out.mean(-1)  # losses.py:74
+    B = out.shape[0]
+    num_nodes = int(np.prod(out.shape[1:]))  # losses.py:77-80
+    out = out.view(B, num_nodes)
+    num_unique = weights.shape[0]
+    num_lon = num_nodes // num_unique  # losses.py:84-85
+    weight_grid = weights.unsqueeze(1).expand(num_unique, num_lon).reshape(1, num_nodes).expand(B, num_nodes)  # losses.py:88-89
+    return (out * weight_grid).mean()  # losses.py:92-95

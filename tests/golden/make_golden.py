@@ -115,6 +115,28 @@ def run_graphcast(R, name="graphcast_10deg_b2"):
                         out=outs[False].numpy(), out_efficient=outs[True].numpy())  # fmt: skip
 
 
+def run_loss(name="loss_5deg"):
+    """NormalizedMSELoss (losses.py:9-94) from the reference's own file on seeded inputs, normalize False and True."""
+    import contextlib
+    import io
+
+    L = ref_shims.load_reference_losses()
+    lat_lons = grid(5)
+    rng = np.random.Generator(np.random.PCG64(11))
+    B, N, F = 3, len(lat_lons), 78
+    pred = torch.from_numpy(rng.standard_normal((B, N, F)).astype(np.float32))
+    target = torch.from_numpy(rng.standard_normal((B, N, F)).astype(np.float32))
+    var = rng.uniform(0.5, 2.0, F).astype(np.float32)
+    vals = {}
+    for normalize in (False, True):
+        crit = L.NormalizedMSELoss(feature_variance=var.tolist(), lat_lons=lat_lons, normalize=normalize)
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints tensor shapes (losses.py:62-67)
+            vals[normalize] = float(crit(pred, target))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), config=json.dumps(dict(step=5, batch=B, seed=11, features=F)),
+                        feature_variance=var, loss_plain=np.float64(vals[False]), loss_normalized=np.float64(vals[True]))  # fmt: skip
+    print(name, vals)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     R = ref_shims.load_reference()
@@ -122,3 +144,4 @@ if __name__ == "__main__":
         run_forecaster(R, n, s)
     run_assimilator(R)
     run_graphcast(R)
+    run_loss()

@@ -186,3 +186,38 @@ def test_graphcast_wrapper_matches_reference_fixture(golden_dir, precision, effi
         strategy(model)
         out = model(x).cpu().numpy()
         assert np.abs(out - ref).max() < TOL
+
+
+@pytest.mark.gpu
+def test_normalized_mse_loss_kernel(golden_dir):
+    """Loss boundary (forward): the CUDA reduction vs the reference fixture and vs the oracle on a 1-degree,
+    batch-8 sized input; shard sums compose to the full-batch loss."""
+    from graph_weather_b200 import NormalizedMSELoss
+    from oracle import restate
+
+    z = np.load(os.path.join(golden_dir, "loss_5deg.npz"))
+    cfg = json.loads(str(z["config"]))
+    lat_lons = [(float(a), float(b)) for a in range(-90, 90, cfg["step"]) for b in range(0, 360, cfg["step"])]
+    rng = np.random.Generator(np.random.PCG64(cfg["seed"]))
+    shape = (cfg["batch"], len(lat_lons), cfg["features"])
+    pred = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    target = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    var = rng.uniform(0.5, 2.0, cfg["features"]).astype(np.float32)
+    for normalize, key in ((False, "loss_plain"), (True, "loss_normalized")):
+        crit = NormalizedMSELoss(var.tolist(), lat_lons, normalize=normalize)
+        got = float(crit(pred.cuda(), target.cuda()))
+        assert abs(got - float(z[key])) <= 2e-6 * float(z[key]), (got, float(z[key]))  # fp32 summation-order tolerance
+        with pytest.raises(RuntimeError):
+            crit(pred, target)  # CPU tensors: no fallback
+    # full size (1 deg, batch 8, 78 features): against the oracle, and shard sums against the whole
+    ll = [(float(a), float(b)) for a in range(-90, 90) for b in range(0, 360)]
+    g = torch.Generator().manual_seed(5)
+    p, t = torch.randn(8, len(ll), 78, generator=g), torch.randn(8, len(ll), 78, generator=g)
+    crit = NormalizedMSELoss(var.tolist(), ll, normalize=True)
+    ref = float(restate.normalized_mse_loss(p, t, var.tolist(), ll, True))
+    pc, tc = p.cuda(), t.cuda()
+    got = float(crit(pc, tc))
+    assert abs(got - ref) <= 5e-6 * ref, (got, ref)
+    s = float(crit.local_sum(pc[:3], tc[:3])) + float(crit.local_sum(pc[3:], tc[3:]))
+    assert abs(s / (8 * len(ll)) - got) <= 1e-6 * got
+    assert float(crit(pc, tc)) == got  # deterministic reduction tree

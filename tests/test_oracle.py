@@ -58,3 +58,38 @@ def test_graphcast_restatement_matches_reference(golden_dir):
     out = restate.forecaster_forward(sd, g, x, feature_dim=78)
     assert np.abs(out.numpy() - z["out"]).max() < 1e-5
     assert np.abs(z["out"] - z["out_efficient"]).max() < 1e-4  # the reference's own tolerance, test_efficient_batching.py:145
+
+
+def _loss_case(golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss_5deg.npz"))
+    cfg = json.loads(str(z["config"]))
+    lat_lons = [(float(a), float(b)) for a in range(-90, 90, cfg["step"]) for b in range(0, 360, cfg["step"])]
+    rng = np.random.Generator(np.random.PCG64(cfg["seed"]))
+    shape = (cfg["batch"], len(lat_lons), cfg["features"])
+    pred = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    target = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    var = rng.uniform(0.5, 2.0, cfg["features"]).astype(np.float32)
+    assert np.array_equal(var, z["feature_variance"])
+    return z, lat_lons, pred, target, var
+
+
+def test_loss_restatement_matches_reference(golden_dir):
+    """oracle.restate.normalized_mse_loss vs NormalizedMSELoss of the reference's own losses.py (fixture made by make_golden.py)."""
+    z, lat_lons, pred, target, var = _loss_case(golden_dir)
+    for normalize, key in ((False, "loss_plain"), (True, "loss_normalized")):
+        got = float(restate.normalized_mse_loss(pred, target, var.tolist(), lat_lons, normalize))
+        assert abs(got - float(z[key])) <= 1e-6 * abs(float(z[key]))
+
+
+def test_loss_shard_sums_compose(golden_dir):
+    """The multi-GPU form of the loss: per-shard sums of w(n) * mean_f(...) added and divided by the global row count equal the
+    loss over the whole batch (what graph_weather_b200.NormalizedMSELoss.forward(group=...) exchanges is one scalar per rank)."""
+    from graph_weather_b200.losses import node_weights
+
+    z, lat_lons, pred, target, var = _loss_case(golden_dir)
+    w = torch.from_numpy(node_weights(lat_lons, pred.shape[1])).double()
+    per_row = (((pred - target) ** 2) / torch.from_numpy(var)).mean(-1).double() * w
+    total = float(per_row[:2].sum() + per_row[2:].sum()) / (pred.shape[0] * pred.shape[1])
+    assert abs(total - float(z["loss_normalized"])) <= 1e-6 * float(z["loss_normalized"])
+    with pytest.raises(RuntimeError):
+        node_weights(lat_lons, pred.shape[1] + 1)

@@ -58,3 +58,11 @@ for prec in ("fp32", "fp32_simt"):
     res[f"assimilator_{prec}"] = {"ms": timeit(lambda: a(f, o)), "shape": list(y.shape), "finite": bool(torch.isfinite(y).all())}
 print(json.dumps(res))
 json.dump(res, open("gpurun_out/config_sweep.json", "w"), indent=1)
+# ---- loss boundary: NormalizedMSELoss at 1 deg, batch 8 (HBM-bound reduction; algorithmic bytes = 2 x 4 x B x N x F)
+from graph_weather_b200 import NormalizedMSELoss
+ll = [(float(a), float(b)) for a in range(-90, 90) for b in range(0, 360)]
+crit = NormalizedMSELoss([1.0 + 0.01 * i for i in range(78)], ll, normalize=True)
+p, t = torch.randn(8, len(ll), 78, device="cuda"), torch.randn(8, len(ll), 78, device="cuda")
+ms = timeit(lambda: crit.local_sum(p, t), iters=20)
+res["loss_1deg_b8"] = {"ms": ms, "GBps": 2 * p.numel() * 4 / ms / 1e6, "value": float(crit(p, t))}
+print(json.dumps(res), flush=True)
