@@ -15,17 +15,22 @@
 // Layout of the work (third generation; the second, with mover warps and shared-memory staging -- git history, profiles/r01_c_* --
 // spent 40 % of its time in mbarrier hand-offs, measured with tools/ablate.py):
 //   * 16 worker warps, four per TMEM lane quadrant.  A worker reads the accumulator with tcgen05.ld.16x256b, whose register
-//     fragment gives four adjacent lanes eight consecutive columns of one row (32 B = one sector).  In that fragment layout
-//     the workers load gathered addends / residual rows and store outputs DIRECTLY from/to global memory with 8-byte
-//     accesses (8 rows x 32 B per warp instruction, every fetched sector fully used): no staging buffers, no mover warps,
-//     no hand-off barriers.  Loads for the next 64-column chunk are issued before the current chunk is converted.
+//     fragment gives four adjacent lanes one row.  The weights are packed with output rows and K columns permuted inside groups
+//     of 16 (perm16, gw_pack.cu) so that a thread's fragment is four CONSECUTIVE features of a row: in that layout the workers
+//     load gathered addends / residual rows and store outputs DIRECTLY from/to global memory with 16-byte accesses (8 rows x 64 B
+//     per warp instruction, every fetched sector fully used): no staging buffers, no mover warps, no hand-off barriers.  Loads
+//     for the next 64-column chunk (global operands and the accumulator chunk itself) are issued while the current one is
+//     converted.
 //   * the A operand ring holds a full K = 256 operand (4 chunks x [128 x 64] hi|lo = 128 KB).  Because a layer's epilogue
 //     starts only when that layer's MMAs have completed, every operand slot is known to be free when the epilogue refills
-//     it: the workers never wait for an "empty" barrier (except when a stage-0 operand is wider than the ring).
-//   * per tile a worker waits on 1 barrier per layer (accumulator complete) and arrives on 1 per produced chunk, one
+//     it: per tile a worker waits on 1 barrier per layer (accumulator complete) and arrives on 1 per produced chunk, one
 //     elected lane per warp.
-//   * the stage-0 operand of the NEXT tile is assembled between the last layer's accumulator-complete wait and its epilogue,
-//     so the tensor pipe runs the next tile's first layer under the LayerNorm epilogue of this tile.
+//   * the stage-0 operand of the NEXT tile is assembled before the current tile's last epilogue, slot by slot as the last
+//     layer's MMAs release them (empty_a): the assembly overlaps the tail of those MMAs, and the tensor pipe then runs the next
+//     tile's first layer on the other accumulator under the LayerNorm epilogue of this tile.
+//   * two instantiations per precision: the lean path (every source / output 16-byte aligned and as wide as the layer; rows are a
+//     warp-uniform 64-bit base + 32-bit offsets; the epilogue is specialised per feature mask) and the general path (any width /
+//     alignment).  setmaxnreg gives the workers 120 registers and the auxiliary warpgroup 32; the lean path has no spills.
 //   * warp 16: weight producer (cp.async.bulk of pre-swizzled 32 KB panels), warp 17: MMA issuer (one thread).
 // TMEM: 512 columns = two 128x256 fp32 accumulators alternating by layer.
 #include <cuda_bf16.h>
