@@ -1,4 +1,8 @@
-"""Dump the in-kernel event timeline (CTA 0) of one tensor-core chain: python tools/trace_chain.py --tag proc_edge"""
+"""Dump the in-kernel event timeline (CTA 0) of one tensor-core chain.  The tracer exists only in the diagnostics build:
+
+    python tools/ablate.py --build-only                      # here, in the build container -> build_abl/libgwb200.so
+    GW_ABLATE=0 python tools/trace_chain.py --tag proc_edge   # on the GPU box (GW_B200_LIB defaults to build_abl/)
+"""
 import argparse, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,6 +11,7 @@ import __graft_entry__ as ge
 ap = argparse.ArgumentParser(); ap.add_argument("--tag", default="proc_edge"); ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--out", default="gpurun_out/trace.npy"); a = ap.parse_args()
 ge.build()
+os.environ.setdefault("GW_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build_abl", "libgwb200.so"))
 from graph_weather_b200 import GraphWeatherForecaster
 ll = [(float(x), float(y)) for x in range(-90, 90) for y in range(0, 360)]
 torch.manual_seed(0)
