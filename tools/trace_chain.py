@@ -10,8 +10,8 @@ import __graft_entry__ as ge
 
 ap = argparse.ArgumentParser(); ap.add_argument("--tag", default="proc_edge"); ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--out", default="gpurun_out/trace.npy"); a = ap.parse_args()
-ge.build()
 os.environ.setdefault("GW_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build_abl", "libgwb200.so"))
+ge.build()
 from graph_weather_b200 import GraphWeatherForecaster
 ll = [(float(x), float(y)) for x in range(-90, 90) for y in range(0, 360)]
 torch.manual_seed(0)
