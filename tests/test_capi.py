@@ -83,3 +83,21 @@ def test_graphcast_wrapper_contract():
     assert (m._checkpoint_encoder, m._checkpoint_processor_segments, m._checkpoint_decoder) == (True, -1, True)
     GraphCastConfig.full_checkpointing(m)
     assert m._checkpoint_model and not m._checkpoint_encoder
+
+
+def test_perm16_feature_order_contract():
+    """The weight packing (csrc/gw_pack.cu, perm16_f) and the chain kernel (csrc/gw_tc3.cu) agree on this map: inside every group
+    of 16 features, packed position a holds logical feature f(a) = 4*((a>>1)&3) + 2*(a>>3) + (a&1).  It must be a permutation,
+    and the four accumulator columns a tcgen05.ld.16x256b.x2 fragment gives lane t -- 2t, 2t+1, 8+2t, 9+2t (t = lane % 4) -- must
+    be four consecutive logical features starting at 4t, which is what makes the 128-bit global accesses of the epilogue legal."""
+
+    def f(a):
+        return (a & ~15) | (4 * ((a >> 1) & 3) + 2 * ((a >> 3) & 1) + (a & 1))
+
+    assert sorted(f(a) for a in range(64)) == list(range(64))
+    for group in (0, 16, 32):
+        for t in range(4):
+            cols = [group + 2 * t, group + 2 * t + 1, group + 8 + 2 * t, group + 9 + 2 * t]
+            assert [f(c) for c in cols] == [group + 4 * t + i for i in range(4)]
+    src = open(os.path.join(ge.ROOT, "graph_weather_b200", "csrc", "gw_pack.cu")).read()
+    assert "(4 * ((a >> 1) & 3) + 2 * ((a >> 3) & 1) + (a & 1))" in src  # the formula the test restates
