@@ -50,3 +50,45 @@ def test_all_gather_even():
 
 def test_all_gather_uneven():
     _run(7)
+
+
+def _loss_worker(rank, world, port, q):
+    """The scalar exchange of NormalizedMSELoss.forward(group=...): each rank reduces its batch shard to one double, the sums are
+    all-reduced and divided by the global row count.  On CPU the per-shard reduction (the CUDA kernel's job) is stood in for by
+    the oracle's arithmetic; everything else is the product code path."""
+    import numpy as np
+
+    from graph_weather_b200.losses import NormalizedMSELoss, node_weights
+    from oracle import restate
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lat_lons = [(float(a), float(b)) for a in range(-90, 90, 30) for b in range(0, 360, 30)]
+    g = torch.Generator().manual_seed(3)
+    total, F = 5, 6
+    pred, target = torch.randn(total, len(lat_lons), F, generator=g), torch.randn(total, len(lat_lons), F, generator=g)
+    var = [0.5 + 0.25 * i for i in range(F)]
+    crit = NormalizedMSELoss(var, lat_lons, normalize=True)
+    w = torch.from_numpy(node_weights(lat_lons, len(lat_lons))).double()
+
+    def cpu_local_sum(p, t):  # stands in for gw_normalized_mse_loss_sum
+        return ((((p - t) ** 2) / torch.tensor(var)).mean(-1).double() * w).sum().reshape(1)
+
+    crit.local_sum = cpu_local_sum
+    a, b = shard_range(total, rank, world)
+    got = float(crit(pred[a:b], target[a:b], group=dist.group.WORLD, total_batch=total))
+    ref = float(restate.normalized_mse_loss(pred, target, var, lat_lons, True))
+    q.put((rank, abs(got - ref) <= 1e-6 * abs(ref), got))
+    dist.destroy_process_group()
+
+
+def test_loss_scalar_exchange_uneven_shards():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_loss_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2]  # every rank holds the same loss
