@@ -1,21 +1,26 @@
-"""bench.py -- forward steps/s of GraphWeatherForecaster(lat_lons)(features) at the 1-degree / 102->78 configuration.
+"""bench.py -- forward steps/s of GraphWeatherForecaster(lat_lons)(features), the reference's README call (README.md:48-58).
 
-    python bench.py --gpus 1 --steps 20 --warmup 3                 # this repo's CUDA path (tcgen05 chains)
-    python bench.py --impl reference --steps 2 --warmup 1           # the reference's CPU path (oracle port) on the host cores
-    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, batch-sharded
+    python bench.py                                                  # BASELINE configs[1]: 1 deg, 102->78, batch 8, default path
+    python bench.py --grid 0.25deg --batch 4 --precision bf16        # BASELINE configs[2]
+    python bench.py --impl reference --steps 2 --warmup 1            # the reference's CPU forward on the host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N [--grid 0.25deg --batch 4 --precision bf16]
 
-One step = one model(features) call at batch 8 per GPU (BASELINE.json configs[1]); `value` is the whole-job aggregate
-(steps of batch 8 per second summed over ranks; weak scaling).  With N > 1 every step ends with the single NCCL
-all-gather of the outputs at the loss boundary; nothing else is communicated.
+The model is built exactly as a user of the reference builds it -- `GraphWeatherForecaster(lat_lons)`, no extra keyword --
+unless --precision names a non-default arithmetic mode.  One step = one model(features) call at `--batch` samples per GPU;
+`value` is the whole-job aggregate (steps per second summed over ranks; weak scaling).  With N > 1 every step ends at the
+loss boundary: `--boundary gather` (default) all-gathers the outputs -- issued on a side stream so that it
+overlaps the next step's forward -- and `--boundary loss` exchanges the fused loss scalar instead.
 
 The JSON line carries the contract keys plus
   roofline      the dominant kernel class by device time, timed live with CUDA events on the launching stream
                 (libgwb200's gw_timing_*), algorithmic FLOPs / time vs the measured dense bf16 peak
-  cpu_baseline  the oracle port of the reference forward timed on this box's host cores (rank 0, N = 1 only)
+  parity        max |GPU - oracle| of one sample of THIS run's output (1 deg grid; the oracle is the CPU restatement)
+  cpu_baseline  the reference forward on this box's host cores, bounded sample (rank 0, N = 1 only)
   e2e           the same metric through the public module call with pinned-host inputs copied in and the forecast copied out
 """
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -43,6 +48,16 @@ def grid_1deg():
     return [(float(lat), float(lon)) for lat in range(-90, 90) for lon in range(0, 360)]  # README.md:48-51
 
 
+def grid_quarter_deg():
+    """ERA5 0.25 degree grid, 721 x 1440: lat = -90 + 0.25 i, lon = 0.25 j."""
+    lat = -90.0 + 0.25 * np.arange(721)
+    lon = 0.25 * np.arange(1440)
+    return np.stack(np.meshgrid(lat, lon, indexing="ij"), axis=-1).reshape(-1, 2)
+
+
+GRIDS = {"1deg": grid_1deg, "0.25deg": grid_quarter_deg}
+
+
 def algorithmic_flops(n, ed):
     """F_alg per sample and per kernel class (live outputs, unfactored Linear FLOPs)."""
     per = {
@@ -56,6 +71,16 @@ def algorithmic_flops(n, ed):
         "dec_node": n * (F_NODE_MLP + F_NODE_DEC),
     }
     return sum(per.values()), per
+
+
+def source_hash():
+    """Hash of the CUDA sources: profiles/traffic.json (ncu dram bytes per launch) is only quoted for the build it measured."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "graph_weather_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -102,53 +127,104 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_inputs(lat_lons, batch, seed=42):
-    """Reference-shaped inputs for the CPU leg: default-initialised weights under the seed the reference tests use."""
-    from graph_weather_b200 import GraphWeatherForecaster, graphs
+def bind_to_gpu_numa(index):
+    """Pins this process (and the pinned host buffers it is about to allocate) to the CPUs NVML reports as local to the GPU,
+    so that the H2D / D2H copies of the end-to-end loop do not cross sockets.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def reference_model_and_inputs(lat_lons, batch, seed=42):
+    """The CPU leg's model: the reference's own unmodified modules (oracle/ref_shims.py) when /root/reference exists (build
+    container), else the oracle port (oracle/restate.py; GPU box).  Default initialisation under the seed the reference tests
+    use; `run(x)` is one forward."""
+    from oracle import ref_shims, restate
+
+    x = None
+    if ref_shims.available():
+        R = ref_shims.load_reference()
+        torch.manual_seed(seed)
+        model = R.GraphWeatherForecaster([tuple(p) for p in np.asarray(lat_lons).tolist()]).eval()
+        x = torch.randn(batch, len(lat_lons), FIN)
+
+        def run(inp):
+            with torch.no_grad():
+                return model(inp)
+
+        return "ref_shims", run, x
+    from graph_weather_b200 import GraphWeatherForecaster
 
     torch.manual_seed(seed)
-    model = GraphWeatherForecaster(lat_lons)  # same init as the reference under the same seed (tests/test_capi.py)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    e, m, d = model.encoder._g_enc, model.encoder._g_lat, model.decoder._g_dec
-    g = dict(enc_edge_index=torch.from_numpy(e.edge_index), enc_edge_attr=torch.from_numpy(e.edge_attr),
-             lat_edge_index=torch.from_numpy(m.edge_index), lat_edge_attr=torch.from_numpy(m.edge_attr),
-             dec_edge_index=torch.from_numpy(d.edge_index), dec_edge_attr=torch.from_numpy(d.edge_attr),
-             num_latlons=len(lat_lons), num_h3=m.num_h3)  # fmt: skip
+    ours = GraphWeatherForecaster(lat_lons)  # same init as the reference under the same seed (tests/test_capi.py)
+    sd = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+    g = oracle_graphs(ours)
     x = torch.randn(batch, len(lat_lons), FIN)
-    return sd, g, x
+
+    def run(inp):
+        return restate.forecaster_forward(sd, g, inp)
+
+    return "port", run, x
 
 
-def time_cpu_reference(lat_lons, step_batch, sample_batch, steps, warmup):
-    """The reference's forward (oracle/restate.py: same ops, same replicated-graph batching) on the host cores.
-    Each timed forward runs `sample_batch` of the step's `step_batch` samples; steps/s = samples/s / step_batch."""
-    from oracle import restate
+def oracle_graphs(model):
+    e, m, d = model.encoder._g_enc, model.encoder._g_lat, model.decoder._g_dec
+    return dict(enc_edge_index=torch.from_numpy(e.edge_index), enc_edge_attr=torch.from_numpy(e.edge_attr),
+                lat_edge_index=torch.from_numpy(m.edge_index), lat_edge_attr=torch.from_numpy(m.edge_attr),
+                dec_edge_index=torch.from_numpy(d.edge_index), dec_edge_attr=torch.from_numpy(d.edge_attr),
+                num_latlons=model.encoder.num_latlons, num_h3=m.num_h3)  # fmt: skip
 
+
+def pick_threads(run, x1):
+    """All logical cores or one thread per physical core, whichever runs a one-sample forward faster."""
     cores = os.cpu_count()
-    sd, g, x = oracle_inputs(lat_lons, sample_batch)
-    # give the CPU path its better thread count: all logical cores or one thread per physical core (probe: one Processor
-    # pass on one sample; the untimed warm-up forwards then run at the chosen setting)
     best_n, best_t = cores, None
-    with torch.no_grad():
-        x1, ei1, ea1 = restate.encoder_forward(sd, g, x[:1])
-        for n in sorted({cores, max(1, cores // 2)}, reverse=True):
-            torch.set_num_threads(n)
-            t0 = time.perf_counter()
-            restate.processor_forward(sd, x1, ei1, ea1, 9)
-            dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best_n, best_t = n, dt
-    torch.set_num_threads(best_n)
-    cores = best_n
-    for _ in range(warmup):
-        restate.forecaster_forward(sd, g, x)
-    ts = []
-    for _ in range(steps):
+    for n in sorted({cores, max(1, cores // 2)}, reverse=True):
+        torch.set_num_threads(n)
         t0 = time.perf_counter()
-        restate.forecaster_forward(sd, g, x)
+        run(x1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_n, best_t = n, dt
+    torch.set_num_threads(best_n)
+    return best_n, best_t
+
+
+def time_cpu_forward(lat_lons, step_batch, sample_batch, steps, warmup, budget_s):
+    """Times `run` on `sample_batch` of the step's `step_batch` samples.  The number of timed forwards is cut so that the leg
+    stays inside `budget_s` seconds; what actually ran is returned."""
+    kind, run, x = reference_model_and_inputs(lat_lons, sample_batch)
+    cores, t1 = pick_threads(run, x[:1])
+    est = t1 * sample_batch
+    did_w = 0
+    for _ in range(warmup):
+        if did_w >= 1 and est * (did_w + 1) > 0.3 * budget_s:
+            break
+        t0 = time.perf_counter()
+        run(x)
+        est = time.perf_counter() - t0
+        did_w += 1
+    ts = []
+    for _ in range(max(1, steps)):
+        if ts and (sum(ts) + est) > budget_s:
+            break
+        t0 = time.perf_counter()
+        run(x)
         ts.append(time.perf_counter() - t0)
+        est = ts[-1]
     t = sum(ts) / len(ts)
-    steps_per_s = (sample_batch / t) / step_batch
-    return steps_per_s, t, cores
+    return dict(kind=kind, cores=cores, seconds_per_forward=t, steps=len(ts), warmup=did_w, steps_per_s=(sample_batch / t) / step_batch)
 
 
 def main():
@@ -157,10 +233,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step (BASELINE configs[1]: 8)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt", "bf16"])
+    ap.add_argument("--grid", default="1deg", choices=sorted(GRIDS))
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: 8 at 1 deg, 4 at 0.25 deg = BASELINE configs[1], [2])")
+    ap.add_argument("--precision", default=None, choices=["auto", "fp32", "fp32_simt", "bf16"],
+                    help="default: auto at 1 deg (the constructor default: fp32-faithful tcgen05), bf16 at 0.25 deg (configs[2])")  # fmt: skip
+    ap.add_argument("--boundary", default="gather", choices=["gather", "gather_sync", "loss"], help="what crosses GPUs at the loss boundary (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle comparison of this run's output")
     a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 8 if a.grid == "1deg" else 4
+    if a.precision is None:
+        a.precision = "auto" if a.grid == "1deg" else "bf16"
 
     # stdout carries exactly one JSON line: anything libraries print in between (NCCL's version banner comes from C code)
     # is sent to stderr by pointing file descriptor 1 there until the line is written
@@ -177,56 +261,72 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    lat_lons = grid_1deg()
-    workload = f"1deg_grid_64800pts_102to78_batch{a.batch}_per_gpu_fp32"
-    cfg = {"workload": workload, "grid": "1deg lat -90..89 x lon 0..359 (README.md:48-51)", "batch_per_gpu": a.batch,
-           "global_batch": a.batch * world, "hidden": 256, "processor_blocks": 9, "parallelism": f"dp{world} (batch shards, one all-gather at the loss boundary)",
-           "cache": "inputs per step 211 MB + weight-constant edge tables 0.9 GB stream through HBM each step (> 126 MB L2); no explicit flush"}  # fmt: skip
+    lat_lons = GRIDS[a.grid]()
+    n_pts = len(lat_lons)
+    cfg = {"workload": None, "grid": {"1deg": "1deg lat -90..89 x lon 0..359 (README.md:48-51)", "0.25deg": "0.25deg ERA5 721 x 1440"}[a.grid],
+           "points": n_pts, "batch_per_gpu": a.batch, "global_batch": a.batch * world, "hidden": 256, "processor_blocks": 9,
+           "parallelism": f"dp{world} (batch shards; loss boundary: {a.boundary})",
+           "cache": f"inputs per step {a.batch * n_pts * FIN * 4 / 1e6:.0f} MB + weight-constant edge tables stream through HBM each step (> 126 MB L2); no explicit flush"}  # fmt: skip
 
     if a.impl == "reference":
         if rank != 0:
             return
-        sample_b = min(2, a.batch)
-        sps, t, cores = time_cpu_reference(lat_lons, a.batch, sample_b, max(1, a.steps), max(0, a.warmup))
-        sample = f"{sample_b} of the {a.batch} samples of a step per timed forward (1deg grid); steps/s = samples/s / {a.batch}"
-        emit(({
-            "impl": "reference", "metric": "forward steps/sec", "value": sps, "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        cfg["workload"] = f"{a.grid}_grid_{n_pts}pts_102to78_batch{a.batch}_per_gpu_f32"
+        if a.grid != "1deg":
+            emit({"impl": "reference", "unavailable": "the reference's replicated-graph decoder materialises ~22 GB fp32 per sample at 0.25 deg (BASELINE.md section 3): not run on CPU"})
+            return
+        # one step = one full forward at the step's batch (measured, not extrapolated); as many steps as fit ~4 minutes
+        r = time_cpu_forward(lat_lons, a.batch, a.batch, max(1, a.steps), max(0, min(a.warmup, 1)), budget_s=200.0)
+        sample = (f"full {a.batch}-sample forward per timed step on the 1deg grid; {r['steps']} timed + {r['warmup']} warm-up forwards actually ran "
+                  f"(requested --steps {a.steps} --warmup {a.warmup}, cut to fit ~4 minutes)")  # fmt: skip
+        emit({
+            "impl": "reference", "metric": "forward steps/sec", "value": r["steps_per_s"], "unit": "steps/s", "n_gpus": a.gpus, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": 1000.0 / r["steps_per_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": r["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-        }))  # fmt: skip
+        })  # fmt: skip
         return
 
     import __graft_entry__ as ge
 
     if rank == 0 or not os.path.exists(ge.LIB):
         ge.build()
-    from graph_weather_b200 import GraphWeatherForecaster, _capi
-    from graph_weather_b200.dist import all_gather_batch
+    from graph_weather_b200 import GraphWeatherForecaster, NormalizedMSELoss, _capi
+    from graph_weather_b200.dist import BoundaryGather
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(42)
-    model = GraphWeatherForecaster(lat_lons, precision=a.precision).to(dev).eval()
-    n, ed = len(lat_lons), int(model.decoder._g_dec.src.size)
+    # the drop-in call of the reference's README (README.md:52): no extra keyword on the default path
+    model = (GraphWeatherForecaster(lat_lons) if a.precision == "auto" else GraphWeatherForecaster(lat_lons, precision=a.precision)).to(dev).eval()
+    n, ed = n_pts, int(model.decoder._g_dec.src.size)
     torch.manual_seed(1234 + rank)
     x_host = torch.randn(a.batch, n, FIN).pin_memory()
     x = x_host.to(dev)
     out_host = torch.empty(a.batch, n, FOUT).pin_memory()
+    gather = BoundaryGather(world * a.batch, dev) if (world > 1 and a.boundary != "loss") else None
+    crit = target = None
+    if world > 1 and a.boundary == "loss":
+        crit = NormalizedMSELoss([1.0] * FOUT, [tuple(p) for p in np.asarray(lat_lons).tolist()], normalize=False)
+        target = torch.zeros(a.batch, n, FOUT, device=dev)
+
+    def boundary(y):
+        if world == 1:
+            return y
+        if crit is not None:
+            return crit(y, target, total_batch=world * a.batch)  # one all-reduced scalar
+        return gather(y, overlap=(a.boundary == "gather"))
 
     def step_resident():
-        y = model(x)
-        if world > 1:
-            y_all = all_gather_batch(y, world * a.batch)  # the one collective: outputs at the loss boundary
-            return y_all
-        return y
+        return boundary(model(x))
 
     # End-to-end step through the public module call: every step copies its inputs in from pinned host memory and its
     # forecast back out.  The copies run on their own streams (double-buffered), so step i+1's input upload and step
@@ -249,8 +349,7 @@ def main():
             ev_in.record(s_in)
         cur.wait_event(ev_in)
         y = model(x_bufs[b])
-        if world > 1:
-            all_gather_batch(y, world * a.batch)
+        boundary(y)
         ev_c = torch.cuda.Event()
         ev_c.record(cur)
         e2e_state["used"][b] = ev_c
@@ -261,6 +360,8 @@ def main():
         return y
 
     def sync_all():
+        if gather is not None:
+            gather.wait()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -273,7 +374,9 @@ def main():
         for _ in range(steps):
             fn()
         cur = torch.cuda.current_stream(dev)
-        cur.wait_stream(s_in), cur.wait_stream(s_out)  # the timed region ends when the last download has landed
+        if gather is not None:
+            gather.wait()  # the timed region ends when the last gather has landed ...
+        cur.wait_stream(s_in), cur.wait_stream(s_out)  # ... and the last download too
         e1.record()
         torch.cuda.synchronize(dev)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -282,7 +385,8 @@ def main():
         sync_all()
         return float(ms.item())
 
-    for _ in range(max(3, a.warmup)):
+    warm = max(3, a.warmup)
+    for _ in range(warm):
         step_resident()
     plan = model._engine.plan
     plan.timing_enable(True)
@@ -299,6 +403,29 @@ def main():
     ms_step = ms_total / a.steps
     value = world * a.steps / (ms_total / 1000.0)
     e2e_value = world * a.steps / (ms_e2e / 1000.0)
+    resolved = model._engine.resolved_precision
+    dtype = {"fp32": "f32 (fp16x2-split tcgen05, fp32 accumulate)", "fp32_tc": "f32 (fp16x2-split tcgen05, fp32 accumulate)",
+             "fp32_simt": "f32", "bf16": "bf16"}[resolved]  # fmt: skip
+    cfg["workload"] = f"{a.grid}_grid_{n_pts}pts_102to78_batch{a.batch}_per_gpu_{'bf16' if resolved == 'bf16' else 'fp32'}"
+    cfg["precision"] = {"requested": a.precision, "resolved": resolved}
+    cfg["plan_gib"] = round(plan.device_bytes() / 2**30, 2)
+
+    # parity of THIS run: one sample of the bench's own batch against the CPU oracle (1 deg; checker only, outside any timing)
+    parity = None
+    if rank == 0 and not a.no_check:
+        if a.grid == "1deg":
+            from oracle import restate
+
+            b = a.batch - 1
+            with torch.no_grad():
+                y = model(x)[b : b + 1].cpu()
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            ref = restate.forecaster_forward(sd, oracle_graphs(model), x_host[b : b + 1])
+            tol = 1e-4 if resolved != "bf16" else 2e-2
+            err = float((y - ref).abs().max())
+            parity = {"max_abs_err": err, "tol": tol, "ok": bool(err < tol), "sample": b, "oracle": "oracle/restate.py (CPU restatement pinned to the reference fixtures)"}
+        else:
+            parity = {"max_abs_err": None, "note": "no CPU oracle at 0.25 deg (22 GB/sample); see tests/test_gpu_parity.py::test_quarter_degree_*"}
 
     if rank != 0:
         if world > 1:
@@ -317,33 +444,36 @@ def main():
     cnt, ms_dom = tags[dom]
     per_launch_flops = per[dom] * a.batch * a.steps / cnt
     achieved = per_launch_flops / ((ms_dom / cnt) * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture of this build (profiles/traffic.json absent or measured on other sources)"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("source_hash") == source_hash() and tj.get("workload") == cfg["workload"]:
+            traffic, traffic_note = tj.get(dom), "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/traffic.json (same sources, same workload)"
     except Exception:
         pass
+    split_note = ("the fp32-faithful path issues 3 fp16 MMAs per product, so frac <= 1/3 x (algorithmic/executed FLOP ratio 1/0.58) = 0.57 of the bf16 peak"
+                  if resolved in ("fp32", "fp32_tc") else "")  # fmt: skip
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": traffic, "peak_source": peak_src,
-                "note": "achieved = algorithmic (unfactored, SURVEY 8(d)) FLOPs per launch / mean launch time; the fp32-faithful path "
-                        "issues 3 fp16 MMAs per product, so frac <= 1/3 x (algorithmic/executed FLOP ratio) of the bf16 peak",
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "note": "achieved = algorithmic (unfactored, SURVEY 8(d)) FLOPs per launch / mean launch time; " + split_note,
                 "whole_step": {"achieved": f_alg * a.batch / (ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                                "frac": f_alg * a.batch / (ms_step * 1e-3) / 1e12 / peak_tf},
                 "per_kernel_ms_per_step": {k: round(v[1] / a.steps, 4) for k, v in tags.items() if v[0]},
                 "kernel_time_share_of_step": round(sum(v[1] for v in tags.values()) / ms_total, 4)}  # fmt: skip
     line = {
-        "metric": "forward steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32 (fp16x2-split tcgen05, fp32 accumulate)", "fp32_simt": "f32", "bf16": "bf16"}[a.precision],
+        "metric": "forward steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
         "data": "synthetic", "config": cfg, "samples_per_s": value * a.batch,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
-                "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
+                "ms_per_step": ms_e2e / a.steps, "numa_bound_cpus": numa_cpus},
+        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "parity": parity,
     }  # fmt: skip
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.grid == "1deg":
         sample_b = min(2, a.batch)
-        sps, t, cores = time_cpu_reference(lat_lons, a.batch, sample_b, 2, 1)
-        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "seconds_per_forward": t,
-                                "sample": f"oracle port of the reference forward, {sample_b} of the {a.batch} samples per forward, 1 warm-up + 2 timed; steps/s = samples/s / {a.batch}"}  # fmt: skip
+        r = time_cpu_forward(lat_lons, a.batch, sample_b, 2, 1, budget_s=40.0)
+        line["cpu_baseline"] = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["cores"], "kind": r["kind"], "seconds_per_forward": r["seconds_per_forward"],
+                                "sample": f"reference forward on {sample_b} of the {a.batch} samples per timed forward ({r['warmup']} warm-up + {r['steps']} timed); steps/s = samples/s / {a.batch}; "
+                                          "`bench.py --impl reference` times the full batch"}  # fmt: skip
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "gw_decoder_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "gw_latent_edge_features": (ctypes.c_int, [_vp, _vp, _vp]),
     "gw_plan_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    "gw_plan_status_peek": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "gw_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "gw_debug_trace_next": (ctypes.c_int, [_vp, _i32, _vp]),
     "gw_timing_enable": (ctypes.c_int, [_vp, _i32]),
@@ -240,6 +241,12 @@ class Plan:
             raise RuntimeError(f"libgwb200 device status {v.value}: " + ("activation outside the fp16 range in precision 'fp32' (use 'fp32_simt'); " if v.value & 1 else "")
                                + ("pipeline timeout; " if v.value & 2 else "") + ("shared memory misaligned" if v.value & 4 else ""))
         return 0
+
+    def peek(self) -> int:
+        """Non-blocking read of the host-mapped status word (kernels completed so far); 0 = ok."""
+        v = _i32(0)
+        _check(self.lib.gw_plan_status_peek(self.handle, ctypes.byref(v)))
+        return int(v.value)
 
     def debug_words(self):
         arr = (_i32 * 64)()

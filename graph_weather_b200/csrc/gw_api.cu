@@ -916,7 +916,6 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
            "graph sizes must be non-negative (n_mesh positive); a standalone sub-module leaves the parts it lacks at 0");
   GW_CHECK(d.in_dim > 0 && d.out_dim > 0 && d.node_dim > 0 && d.edge_dim > 0, "feature sizes must be positive");
   GW_CHECK(d.hidden_layers_node >= 1 && d.hidden_layers_edge >= 1 && d.hidden_layers_dec >= 1, "hidden_layers must be >= 1");
-  GW_CHECK(d.node_dim <= 256 && d.edge_dim <= 256, "LayerNorm rows wider than 256 are not supported");
   GW_CHECK(d.residual_dim == 0 || d.residual_dim == d.out_dim,
            "residual_dim must equal out_dim (the reference adds start features of the same width, decoder.py:93)");
   GW_CHECK(d.max_batch >= 1, "max_batch must be >= 1");
@@ -938,7 +937,18 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   }
   gw_plan* p = new gw_plan();
   p->d = d;
-  GW_CUDA(cudaGetDevice(&p->device));
+  // every failure after this point releases the plan and whatever it already holds
+#define GW_CUDA_P(expr)                                                          \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      std::string _m = std::string(#expr) + ": " + cudaGetErrorString(_e);       \
+      gw_plan_destroy(p);                                                        \
+      gw::set_error(_m);                                                         \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+  GW_CUDA_P(cudaGetDevice(&p->device));
   const size_t Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, Hn = d.hidden_node;
   const size_t max_hid = std::max({Dn, De, He, Hn, (size_t)d.hidden_dec, (size_t)d.out_dim});
   const size_t max_rows = std::max({(size_t)d.n_in, (size_t)d.n_out, (size_t)d.n_mesh, (size_t)d.n_lat_edges, (size_t)d.n_dec_edges});
@@ -946,6 +956,10 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   const size_t per_sample = (2 * max_rows * max_hid + std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De +
                              std::max((size_t)d.n_in, (size_t)d.n_out) * Dn) * sizeof(float);
   size_t chunk = std::max<size_t>(1, std::min<size_t>(d.max_batch, (48ull << 30) / std::max<size_t>(per_sample, 1)));
+  if (const char* force = getenv("GW_B200_CHUNK")) {  // test knob: exercise the chunked stage loops on small grids
+    const long v = atol(force);
+    if (v >= 1) chunk = std::min<size_t>((size_t)v, (size_t)d.max_batch);
+  }
   p->chunk = (int)chunk;
   const size_t B = d.max_batch;
   int rc = 0;
@@ -976,10 +990,11 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
     gw::set_error(keep);
     return 1;
   }
-  GW_CUDA(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
-  GW_CUDA(cudaHostAlloc((void**)&p->tc_status_host, 64 * sizeof(int32_t), cudaHostAllocMapped));
+  GW_CUDA_P(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
+  GW_CUDA_P(cudaHostAlloc((void**)&p->tc_status_host, 64 * sizeof(int32_t), cudaHostAllocMapped));
   std::memset(p->tc_status_host, 0, 64 * sizeof(int32_t));
-  GW_CUDA(cudaHostGetDevicePointer((void**)&p->tc_status_dev, p->tc_status_host, 0));
+  GW_CUDA_P(cudaHostGetDevicePointer((void**)&p->tc_status_dev, p->tc_status_host, 0));
+#undef GW_CUDA_P
   p->n_in_cur = d.n_in;
   *out_plan = p;
   return 0;
@@ -1139,6 +1154,12 @@ int gw_plan_status(gw_plan* p, int32_t* status_out, void* stream) {
     return 1;
   }
   if (h[0]) h[0] = 0;
+  return 0;
+}
+
+int gw_plan_status_peek(gw_plan* p, int32_t* status_out) {
+  GW_CHECK(p && status_out, "null argument");
+  *status_out = ((volatile int32_t*)p->tc_status_host)[0];  // host-mapped word: no CUDA call, no synchronisation
   return 0;
 }
 

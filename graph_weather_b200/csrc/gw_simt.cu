@@ -220,11 +220,50 @@ cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst,
   return cudaGetLastError();
 }
 
+// Rows wider than one CTA column block (N > 256, e.g. the 1024-wide models of train/run.py:491-501): the row op above runs
+// without its LayerNorm / residual and this kernel finishes the rows in place: out = residual + LN(out).  One warp per row,
+// two passes over the (L2-resident) row like torch's LayerNorm (mean, then biased variance, eps 1e-5).
+__global__ void __launch_bounds__(256) gw_ln_rows_kernel(const GemmOp op) {
+  const int lane = threadIdx.x & 31;
+  const long long R = (long long)op.rows_per_sample * op.batch;
+  const long long gr = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gr >= R) return;
+  const int b = (int)(gr / op.rows_per_sample), li = (int)(gr - (long long)b * op.rows_per_sample);
+  float* row = op.out + (size_t)gr * op.ldo;
+  const int N = op.N;
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) s += row[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)N;
+  float q = 0.f;
+  for (int c = lane; c < N; c += 32) {
+    const float d = row[c] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)N + 1e-5f);
+  for (int c = lane; c < N; c += 32) {
+    float x = (row[c] - mean) * rstd * __ldg(op.ln_gamma + c) + __ldg(op.ln_beta + c);
+    if (op.residual.kind != SRC_NONE) x += fetch_src(op.residual, b, li, c);
+    row[c] = x;
+  }
+}
+
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream) {
   const long long R = (long long)op.rows_per_sample * op.batch;
   if (R <= 0 || op.N <= 0) return cudaSuccess;
-  if (op.ln_gamma && op.N > BN) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)((op.N + BN - 1) / BN));
+  if (op.ln_gamma && op.N > BN) {
+    GemmOp g = op;  // GEMM + bias + addends + ReLU only; LayerNorm and residual in the second kernel
+    g.ln_gamma = g.ln_beta = nullptr;
+    g.residual = RowSrc();
+    gw_rowop_f32_kernel<<<grid, NT, 0, stream>>>(g);
+    gw_ln_rows_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>(op);
+    count_launch(2);
+    return cudaGetLastError();
+  }
   gw_rowop_f32_kernel<<<grid, NT, 0, stream>>>(op);
   count_launch();
   return cudaGetLastError();

@@ -41,11 +41,11 @@ class NormalizedMSELoss(torch.nn.Module):
         assert not torch.isnan(self.weights).any()
         self._dev = {}  # per device: (inv_variance, node_weight, workspace, sum)
 
-    def _device_state(self, device, num_nodes):
-        key = (str(device), num_nodes)
+    def _device_state(self, device, num_nodes, num_features):
+        key = (str(device), num_nodes, num_features)
         if key not in self._dev:
             lib = _capi.load()
-            inv = (1.0 / self.feature_variance.to(torch.float32)).to(device).contiguous()
+            inv = (1.0 / self.feature_variance.to(torch.float32)).reshape(-1).expand(num_features).to(device).contiguous()
             w = torch.from_numpy(node_weights(self.lat_lons, num_nodes)).to(device)
             ws = torch.empty(int(lib.gw_loss_workspace_bytes()), dtype=torch.uint8, device=device)
             s = torch.zeros(1, dtype=torch.float64, device=device)
@@ -62,11 +62,14 @@ class NormalizedMSELoss(torch.nn.Module):
         F = pred.shape[-1]
         B = pred.shape[0]
         num_nodes = int(np.prod(pred.shape[1:-1]))
-        if self.normalize and self.feature_variance.numel() != F:
+        if self.normalize and self.feature_variance.numel() not in (1, F):  # a 1-element variance broadcasts (losses.py:70)
             raise RuntimeError("feature_variance does not match the feature dimension")
         p = pred.detach().to(torch.float32).contiguous()
         t = target.detach().to(torch.float32).contiguous()
-        inv, w, ws, s = self._device_state(pred.device, num_nodes)
+        inv, w, ws, s = self._device_state(pred.device, num_nodes, F)
+        if B == 0:  # an empty batch shard (total_batch < world size) contributes nothing; the kernel is not launched
+            s.zero_()
+            return s
         with torch.cuda.device(pred.device):
             st = torch.cuda.current_stream().cuda_stream
             _capi._check(lib.gw_normalized_mse_loss_sum(
@@ -79,11 +82,24 @@ class NormalizedMSELoss(torch.nn.Module):
         """losses.py:46-94.  With `group` (torch.distributed), `pred` / `target` are this rank's batch shard and the result is
         the loss over the whole batch of `total_batch` samples: the ranks exchange one scalar."""
         s = self.local_sum(pred, target)
-        rows = pred.shape[0] * int(np.prod(pred.shape[1:-1]))
+        nodes = int(np.prod(pred.shape[1:-1]))
+        rows = pred.shape[0] * nodes
         if group is not None or total_batch is not None:
             import torch.distributed as dist
 
+            if total_batch is None:  # derive the global batch from the shards: [sum, local batch] reduced together
+                s = torch.cat([s, torch.tensor([float(pred.shape[0])], dtype=torch.float64, device=s.device)])
+                dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+                return (s[0] / (s[1] * nodes)).to(torch.float32).reshape(())
             s = s.clone()
             dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-            rows = int(total_batch) * int(np.prod(pred.shape[1:-1]))
-        return (s / rows).to(torch.float32).reshape(())
+            rows = int(total_batch) * nodes
+        out = (s / rows).to(torch.float32).reshape(())
+        return out
+
+    def checked(self, pred: torch.Tensor, target: torch.Tensor, **kw):
+        """forward + the reference's NaN assertion on the result (losses.py:59-62,93 assert on every intermediate; a NaN in
+        any of them makes the result NaN).  Synchronises; use in debugging runs."""
+        out = self.forward(pred, target, **kw)
+        assert not torch.isnan(out).any()
+        return out

@@ -113,15 +113,45 @@ def _params_fingerprint(named):
     return tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in named)
 
 
+def _tc_eligible(dims: dict) -> bool:
+    """The tcgen05 chains are built for the reference's default sizes: 256-wide node / edge / hidden, 2 hidden layers."""
+    return (dims.get("node_dim") == 256 and dims.get("edge_dim") == 256 and dims.get("hidden_node") == 256
+            and dims.get("hidden_edge") == 256 and dims.get("hidden_layers_node") == 2 and dims.get("hidden_layers_edge") == 2)  # fmt: skip
+
+
+def _validate_precision(precision: str, dims: dict):
+    """Constructor-time check, so that an impossible request fails where the module is built, not at the first forward."""
+    if precision not in ("auto",) + tuple(_capi.PRECISIONS):
+        raise ValueError(f"precision={precision!r}: expected one of 'auto', {sorted(_capi.PRECISIONS)}")
+    if precision in ("fp32", "fp32_tc", "bf16") and not _tc_eligible(dims):
+        raise ValueError(
+            f"precision={precision!r} runs the tcgen05 chains, which are built for node/edge/hidden dims of 256 and 2 hidden "
+            "layers (the reference defaults); use precision='auto' (CUDA-core exact fp32 for other sizes) or 'fp32_simt'"
+        )
+
+
+def resolve_precision(precision: str, dims: dict, device) -> str:
+    """'auto' (the default of every constructor): the fp32-faithful tcgen05 path wherever it applies -- reference default
+    sizes on an sm_100 device -- and the exact-fp32 CUDA-core path otherwise.  Explicit values are returned unchanged."""
+    if precision != "auto":
+        return precision
+    if _tc_eligible(dims) and torch.cuda.get_device_capability(device)[0] == 10:
+        return "fp32"
+    return "fp32_simt"
+
+
 class _Engine:
     """Creates the plan lazily on the device of the first input, uploads graphs once and weights whenever a parameter
     changed (in-place optimiser steps and load_state_dict bump tensor versions; .to() changes data pointers)."""
 
     def __init__(self, dims: dict, precision: str):
+        _validate_precision(precision, dims)
         self.dims = dict(dims)
         self.precision = precision
+        self.resolved_precision: Optional[str] = None
         self.plan: Optional[_capi.Plan] = None
         self.graph_uploaders = []  # callables(plan)
+        self.generation = 0  # bumped whenever a new plan is created: per-plan upload caches key on it, never on pointers
         self._wfp = None
 
     def _create(self, device, max_batch):
@@ -129,8 +159,10 @@ class _Engine:
             self.plan.close()
         d = dict(self.dims)
         d["max_batch"] = int(max_batch)
-        d["precision"] = _capi.PRECISIONS[self.precision]
+        self.resolved_precision = resolve_precision(self.precision, self.dims, device)
+        d["precision"] = _capi.PRECISIONS[self.resolved_precision]
         self.plan = _capi.Plan(device, **d)
+        self.generation += 1
         for up in self.graph_uploaders:
             up(self.plan)
         self._wfp = None
@@ -149,6 +181,8 @@ class _Engine:
                     need_new = True
         if not need_new and batch > self.plan.dims.max_batch:
             need_new = True
+        if not need_new and self.plan.peek():
+            self.plan.status()  # a kernel of an earlier call flagged a fault: synchronise, clear and raise now
         if need_new:
             self._create(device, max(batch, self.plan.dims.max_batch if self.plan is not None else 1))
         named = list(named_params)
@@ -163,8 +197,11 @@ class _Engine:
 
 
 def _maybe_check(plan):
-    """GW_B200_CHECK=1: synchronise after every forward and raise on a non-zero device status word (tests, debugging)."""
-    if os.environ.get("GW_B200_CHECK", "0") == "1":
+    """Every forward ends with a non-blocking look at the plan's host-mapped status word; a non-zero word (fp16-range
+    overflow, pipeline timeout, misalignment: include/gw_b200.h) escalates to the synchronising `plan.status()`, which
+    raises.  Kernels still running when this returns are covered by the same look at the start of the next call
+    (`_Engine.ensure`).  GW_B200_CHECK=1 synchronises after every forward (tests, debugging)."""
+    if os.environ.get("GW_B200_CHECK", "0") == "1" or plan.peek():
         plan.status()
 
 
@@ -183,7 +220,7 @@ class Encoder(nn.Module):
     def __init__(self, lat_lons: list, resolution: int = 2, input_dim: int = 78, output_dim: int = 256, output_edge_dim: int = 256,
                  hidden_dim_processor_node=256, hidden_dim_processor_edge=256, hidden_layers_processor_node=2,
                  hidden_layers_processor_edge=2, mlp_norm_type="LayerNorm", use_checkpointing: bool = False,
-                 efficient_batching: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+                 efficient_batching: bool = False, precision: str = "auto"):  # fmt: skip
         super().__init__()
         self.use_checkpointing = use_checkpointing  # accepted for API parity; forward-only path keeps no activations
         self.efficient_batching = efficient_batching
@@ -207,6 +244,7 @@ class Encoder(nn.Module):
             hidden_dec=1, hidden_layers_dec=1, num_blocks=1,
         )  # fmt: skip
         self._engine = None
+        _validate_precision(precision, self._dims)
         self._precision = precision
         self._lat_edge_index_t = {}
 
@@ -258,7 +296,7 @@ class Processor(nn.Module):
     def __init__(self, input_dim: int = 256, edge_dim: int = 256, num_blocks: int = 9, hidden_dim_processor_node: int = 256,
                  hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
                  mlp_norm_type: str = "LayerNorm", use_thermalizer: bool = False, use_checkpointing: bool = False,
-                 precision: str = "fp32_simt"):  # fmt: skip
+                 precision: str = "auto"):  # fmt: skip
         super().__init__()
         if use_thermalizer:
             raise NotImplementedError("use_thermalizer=True: the stochastic ThermalizerLayer is outside the accelerated path")
@@ -271,22 +309,21 @@ class Processor(nn.Module):
         self._cfg = dict(node_dim=input_dim, edge_dim=edge_dim, hidden_node=hidden_dim_processor_node,
                          hidden_edge=hidden_dim_processor_edge, hidden_layers_node=hidden_layers_processor_node,
                          hidden_layers_edge=hidden_layers_processor_edge, num_blocks=num_blocks)  # fmt: skip
+        _validate_precision(precision, self._cfg)
         self._precision = precision
         self._engine = None
-        self._graph_cache = None
 
     def set_checkpoint_segments(self, checkpoint_segments: int):
         self.checkpoint_segments = checkpoint_segments
 
     def _sorted_graph(self, edge_index, n_nodes):
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n_nodes)
-        if self._graph_cache is None or self._graph_cache[0] != key:
-            dst_sorted, order = torch.sort(edge_index[1], stable=True)
-            src = edge_index[0][order].to(torch.int32).contiguous()
-            ptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=edge_index.device)
-            ptr[1:] = torch.cumsum(torch.bincount(dst_sorted, minlength=n_nodes), 0).to(torch.int32)
-            self._graph_cache = (key, src, dst_sorted.to(torch.int32).contiguous(), ptr, order)
-        return self._graph_cache[1:]
+        """Target-sorted int32 view of a caller-supplied graph.  Rebuilt on every call, as the reference re-reads its
+        edge_index argument every call (processor.py:83-128): a cache keyed on the tensor's address would go stale when the
+        allocator recycles it.  No host synchronisation: sort + searchsorted on the device."""
+        dst_sorted, order = torch.sort(edge_index[1], stable=True)
+        src = edge_index[0][order].to(torch.int32).contiguous()
+        ptr = torch.searchsorted(dst_sorted, torch.arange(n_nodes + 1, device=edge_index.device, dtype=dst_sorted.dtype)).to(torch.int32)
+        return src, dst_sorted.to(torch.int32).contiguous(), ptr.contiguous(), order
 
     def forward(self, x: torch.Tensor, edge_index, edge_attr, t: int = 0, batch_size: int = None, efficient_batching: bool = False):
         if x.device.type != "cuda":
@@ -319,7 +356,7 @@ class AssimilatorDecoder(nn.Module):
                  hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
                  hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", hidden_dim_decoder: int = 128,
                  hidden_layers_decoder: int = 2, use_checkpointing: bool = False, efficient_batching: bool = False,
-                 precision: str = "fp32_simt"):  # fmt: skip
+                 precision: str = "auto"):  # fmt: skip
         super().__init__()
         self.use_checkpointing = use_checkpointing
         self.efficient_batching = efficient_batching
@@ -340,6 +377,7 @@ class AssimilatorDecoder(nn.Module):
             hidden_layers_node=hidden_layers_processor_node, hidden_layers_edge=hidden_layers_processor_edge,
             hidden_dec=hidden_dim_decoder, hidden_layers_dec=hidden_layers_decoder, num_blocks=1,
         )  # fmt: skip
+        _validate_precision(precision, self._dims)
         self._precision = precision
         self._engine = None
 
@@ -374,7 +412,7 @@ class Decoder(AssimilatorDecoder):
                  hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
                  hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", hidden_dim_decoder: int = 128,
                  hidden_layers_decoder: int = 2, use_checkpointing: bool = False, efficient_batching: bool = False,
-                 precision: str = "fp32_simt"):  # fmt: skip
+                 precision: str = "auto"):  # fmt: skip
         super().__init__(lat_lons, resolution, input_dim, output_dim, output_edge_dim, hidden_dim_processor_node,
                          hidden_dim_processor_edge, hidden_layers_processor_node, hidden_layers_processor_edge, mlp_norm_type,
                          hidden_dim_decoder, hidden_layers_decoder, use_checkpointing, efficient_batching, precision)  # fmt: skip
@@ -397,7 +435,7 @@ class AssimilatorEncoder(nn.Module):
     def __init__(self, resolution: int = 2, input_dim: int = 2, output_dim: int = 256, output_edge_dim: int = 256,
                  hidden_dim_processor_node: int = 256, hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2,
                  hidden_layers_processor_edge: int = 2, mlp_norm_type: str = "LayerNorm", use_checkpointing: bool = False,
-                 precision: str = "fp32_simt"):  # fmt: skip
+                 precision: str = "auto"):  # fmt: skip
         super().__init__()
         self.use_checkpointing = use_checkpointing
         self.output_dim = output_dim
@@ -418,6 +456,7 @@ class AssimilatorEncoder(nn.Module):
             hidden_layers_node=hidden_layers_processor_node, hidden_layers_edge=hidden_layers_processor_edge,
             hidden_dec=1, hidden_layers_dec=1, num_blocks=1,
         )  # fmt: skip
+        _validate_precision(precision, self._dims)
         self._precision = precision
         self._engine = None
         self.efficient_batching = False
@@ -428,15 +467,14 @@ class AssimilatorEncoder(nn.Module):
         m = self._g_lat
         plan.set_latent_graph(m.src, m.dst, m.ptr, m.edge_attr[m.perm])
 
-    def _input_graph(self, lat_lon_heights):
-        """create_input_graph (assimilator_encoder.py:170-216), rebuilt when the observation set changes."""
-        llh = lat_lon_heights.detach().cpu().numpy().astype(np.float64)
-        return graphs.build_encoder_graph(llh[:, :2], self.resolution, heights=llh[:, 2])
-
-    def _upload_obs(self, plan, lat_lon_heights):
-        key = (lat_lon_heights.data_ptr(), lat_lon_heights._version, tuple(lat_lon_heights.shape), plan.handle.value)
+    def _upload_obs(self, engine, plan, lat_lon_heights):
+        """The reference rebuilds the observation graph on every forward (assimilator_encoder.py:118,170-216).  Here the
+        upload is skipped only when the observation set is provably the same: the key is the CONTENT of lat_lon_heights
+        (it is copied to the host to build the graph anyway) plus the engine's plan generation, never a tensor address."""
+        llh = lat_lon_heights.detach().to(device="cpu", dtype=torch.float64).contiguous().numpy()
+        key = (engine.generation, llh.shape, hash(llh.tobytes()))
         if key != self._obs_key:
-            g = self._input_graph(lat_lon_heights)
+            g = graphs.build_encoder_graph(llh[:, :2], self.resolution, heights=llh[:, 2])
             plan.set_encoder_graph(g.mesh_local, g.perm, g.ptr, g.edge_attr)
             self._obs_key = key
 
@@ -454,7 +492,7 @@ class AssimilatorEncoder(nn.Module):
         B, nobs = features.shape[0], lat_lon_heights.shape[0]
         eng = self._own_engine()
         plan = eng.ensure(features.device, B, _prefixed("encoder", self), grow=dict(n_in=nobs))
-        self._upload_obs(plan, lat_lon_heights)
+        self._upload_obs(eng, plan, lat_lon_heights)
         f = features.detach().to(torch.float32).contiguous()
         x = torch.empty((B * self.num_h3, self.output_dim), dtype=torch.float32, device=f.device)
         plan.encoder_forward(f, x)
@@ -501,7 +539,7 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
                  hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
                  hidden_dim_decoder: int = 128, hidden_layers_decoder: int = 2, norm_type: str = "LayerNorm",
                  use_checkpointing: bool = False, constraint_type: str = "none", use_thermalizer: bool = False,
-                 precision: str = "fp32_simt"):  # fmt: skip
+                 precision: str = "auto"):  # fmt: skip
         super().__init__()
         if constraint_type != "none":
             raise NotImplementedError("constraint_type != 'none' (PhysicalConstraintLayer) is not on the accelerated path yet")
@@ -595,7 +633,7 @@ class GraphWeatherAssimilator(nn.Module, PyTorchModelHubMixin):
                  node_dim: int = 256, edge_dim: int = 256, num_blocks: int = 9, hidden_dim_processor_node: int = 256,
                  hidden_dim_processor_edge: int = 256, hidden_layers_processor_node: int = 2, hidden_layers_processor_edge: int = 2,
                  hidden_dim_decoder: int = 128, hidden_layers_decoder: int = 2, norm_type: str = "LayerNorm",
-                 use_checkpointing: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+                 use_checkpointing: bool = False, precision: str = "auto"):  # fmt: skip
         super().__init__()
         output_lat_lons = _latlon_list(output_lat_lons)
         self.encoder = AssimilatorEncoder(resolution=resolution, input_dim=observation_dim, output_dim=node_dim,
@@ -630,7 +668,7 @@ class GraphWeatherAssimilator(nn.Module, PyTorchModelHubMixin):
         B, nobs = features.shape[0], obs_lat_lon_heights.shape[0]
         named = [(k, v) for k, v in self.state_dict(keep_vars=True).items()]
         plan = self._engine.ensure(features.device, B, named, grow=dict(n_in=nobs))
-        self.encoder._upload_obs(plan, obs_lat_lon_heights)
+        self.encoder._upload_obs(self._engine, plan, obs_lat_lon_heights)
         f = features.detach().to(torch.float32).contiguous()
         out = torch.empty((B, self.decoder.num_latlons, self.analysis_dim), dtype=torch.float32, device=f.device)
         plan.forward(f, out)
@@ -650,7 +688,7 @@ class GraphCast(nn.Module):
 
     def __init__(self, lat_lons: list, resolution: int = 2, input_dim: int = 78, output_dim: int = 78, hidden_dim: int = 256,
                  num_processor_blocks: int = 9, hidden_layers: int = 2, mlp_norm_type: str = "LayerNorm",
-                 use_checkpointing: bool = False, efficient_batching: bool = False, precision: str = "fp32_simt"):  # fmt: skip
+                 use_checkpointing: bool = False, efficient_batching: bool = False, precision: str = "auto"):  # fmt: skip
         super().__init__()
         lat_lons = _latlon_list(lat_lons)
         self.lat_lons = lat_lons

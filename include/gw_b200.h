@@ -123,6 +123,10 @@ int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
  * bit 0: an activation left the fp16 range in GW_PREC_FP32_TC (results invalid: rerun with GW_PREC_FP32_SIMT);
  * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment.  Non-zero must be treated as failure. */
 int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
+/* Non-blocking read of the same word (it lives in host-mapped memory): reflects every kernel that has COMPLETED so far
+ * and does not clear it.  The Python wrappers peek before and after every forward and escalate to gw_plan_status
+ * (synchronise, clear, raise) when it is non-zero, so a fault is reported at the latest on the next call. */
+int gw_plan_status_peek(gw_plan* plan, int32_t* status_out);
 /* Raw copy of the plan's 64-word host-mapped status block (no CUDA call: usable after a device fault):
  * word 0 = status flags; words 4+3w.. = {barrier byte offset, parity, block} of the wait warp w timed out on. */
 int gw_plan_debug(gw_plan* plan, int32_t* out64);
