@@ -238,8 +238,9 @@ class Plan:
         with torch.cuda.device(self.device):
             _check(self.lib.gw_plan_status(self.handle, ctypes.byref(v), _stream(self.device)))
         if v.value:
-            raise RuntimeError(f"libgwb200 device status {v.value}: " + ("activation outside the fp16 range in precision 'fp32' (use 'fp32_simt'); " if v.value & 1 else "")
-                               + ("pipeline timeout; " if v.value & 2 else "") + ("shared memory misaligned" if v.value & 4 else ""))
+            raise RuntimeError(f"libgwb200 device status {v.value}: " + ("an operand left the fp16 range despite range scaling in precision 'fp32' (use 'fp32_simt'); " if v.value & 1 else "")
+                               + ("pipeline timeout; " if v.value & 2 else "") + ("shared memory misaligned; " if v.value & 4 else "")
+                               + ("a magnitude bound is not finite: the inputs contain inf / nan or overflow fp32" if v.value & 8 else ""))
         return 0
 
     def peek(self) -> int:

@@ -60,6 +60,9 @@ struct Mlp {  // views into the plan-owned weight buffer; Linear l: W[l] [out_l,
   std::vector<int> in, out;
   const float* ln_g = nullptr;
   const float* ln_b = nullptr;
+  // magnitudes (filled by pack_tc_weights; tensor-core chains only): max |b[l]|, and the bound of the LayerNorm'd row
+  std::vector<float> bmax;
+  float ln_bound = 0.f;  // sqrt(out) * max|gamma| + max|beta|
 };
 
 template <class T>
@@ -121,7 +124,7 @@ struct gw_plan {
   DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
   size_t total_bytes = 0;
   // tensor-core path: packed weight images (UMMA operand layout) and their descriptors
-  struct TcW { const void* p = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; };
+  struct TcW { const void* p = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; float gain = 0.f; };  // gain = K * max|W|: |A.W^T| <= gain * max|A|
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
@@ -134,6 +137,14 @@ struct gw_plan {
   DevBuf<float> agg_mesh;     // [max_batch*n_mesh, De] per-mesh-node aggregation (segment sums) of the encoder / processor blocks
   DevBuf<float> agg_grid;     // [chunk*n_out, De] per-lat/lon-point aggregation of the decoder block
   std::vector<TcMlp> tc_proc_edge, tc_proc_node;
+  // operand range of the tensor-core chains: one device float per tensor = a rigorous bound of its magnitudes (SL_*)
+  DevBuf<float> bounds;
+  // fused per-target sums (gw_tc3.cu F_SEG): target of every decoder edge, carry rows of segments cut by a tile quadrant
+  DevBuf<int32_t> dec_dst;
+  DevBuf<float> seg_carry;
+  DevBuf<int> deg_stats;
+  int enc_maxdeg = 0, lat_maxdeg = 0, lat_mindeg = 0, dec_maxdeg = 0, dec_mindeg = 0;
+  bool fuse_seg = true;
   // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
   bool timing = false;
   int cur_tag = 0;
@@ -176,6 +187,21 @@ static RowSrc src_gather_bcast_relu(const float* base, int ld, int width, const 
   s.kind = SRC_GATHER_BCAST_RELU, s.base = base, s.ld = ld, s.width = width, s.idx = idx, s.src_rows = src_rows;
   s.base2 = base2, s.ld2 = ld2;
   return s;
+}
+
+// magnitude-bound slots (gw_plan::bounds)
+enum BoundSlot { SL_FEAT = 0, SL_XIN, SL_XOUT, SL_X0, SL_X1, SL_E0, SL_E1, SL_EIN, SL_P, SL_AGG_MESH, SL_AGG_GRID, SL_ROWS_N, SL_ROWS_E,
+                 SL_EENC, SL_C1ENC, SL_XM0, SL_ELAT, SL_EDEC, SL_E1DEC, SL_COUNT };
+static float* sl(gw_plan* p, int i) { return p->bounds.p + i; }
+static RowSrc bounded(RowSrc s, const float* b, float mul = 1.f) {
+  s.bound = b, s.bound_mul = mul;
+  return s;
+}
+// |x| of a raw caller tensor -> slot (the slot is reset first: absmax accumulates with atomicMax)
+static int raw_bound(gw_plan* p, int slot, const float* x, long long n, cudaStream_t st) {
+  GW_CUDA(cudaMemsetAsync(sl(p, slot), 0, sizeof(float), st));
+  GW_CUDA(launch_absmax_flat(x, n, sl(p, slot), st));
+  return 0;
 }
 
 enum KernelTag { TAG_CONST = 0, TAG_ENC_GRID, TAG_ENC_MESH, TAG_PROC_P, TAG_PROC_EDGE, TAG_PROC_NODE, TAG_DEC_P, TAG_DEC_EDGE,
@@ -248,16 +274,18 @@ static int run_chain(gw_plan* p, TcChain& ch, cudaStream_t st) {
 }
 static bool is_tc(const gw_plan* p) { return p->d.precision != GW_PREC_FP32_SIMT; }
 
-static TcLayer tc_layer(const gw_plan::TcW& w, const float* bias, bool relu, bool feeds) {
+// layer = Linear `w` (+ bias b[l] of MLP m when l >= 0) (+ ReLU); magnitudes for the operand-range ladder travel along
+static TcLayer tc_layer(const gw_plan::TcW& w, const Mlp* m, int l, bool relu, bool feeds) {
   TcLayer L;
   L.Wp = w.p, L.K = w.K, L.N = w.N, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
-  L.bias = bias, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
+  L.bias = (m && l >= 0) ? m->b[l] : nullptr, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
+  L.gain = w.gain, L.off = (m && l >= 0 && (size_t)l < m->bmax.size()) ? m->bmax[l] : 0.f;
   return L;
 }
 static void tc_ln(TcLayer& L, const Mlp& m, const RowSrc& residual) {
-  L.ln_g = m.ln_g, L.ln_b = m.ln_b, L.residual = residual;
+  L.ln_g = m.ln_g, L.ln_b = m.ln_b, L.residual = residual, L.ln_bound = m.ln_bound;
 }
-static void tc_out(TcLayer& L, float* out, int ldo, int cols) { L.out = out, L.ldo = ldo, L.out_cols = cols; }
+static void tc_out(TcLayer& L, float* out, int ldo, int cols, float* bound = nullptr) { L.out = out, L.ldo = ldo, L.out_cols = cols, L.out_bound = bound; }
 
 // Runs an MLP whose first Linear is described by `first` (A sources / addends / weight slice already set; its
 // W/K/ldw/bias may have been overridden by the caller for factored layer 1) and whose remaining layers stream
@@ -427,17 +455,38 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
       tail(md, p->tc_dec_out);
     }
   }
-  const size_t n = reqs.size();
-  GW_TRY(p->tc_absmax.alloc(n));
-  GW_CUDA(cudaMemsetAsync(p->tc_absmax.p, 0, n * sizeof(float), st));
+  // bias / LayerNorm parameter magnitudes of every MLP a chain runs (operand-range ladder, gw_tc3.cu)
+  struct VReq { const float* v; int n; Mlp* m; int what, l; };  // what: 0 = bias l, 1 = gamma, 2 = beta
+  std::vector<VReq> vreqs;
+  auto want_mlp = [&](Mlp& m) {
+    m.bmax.assign(m.L + 1, 0.f);
+    m.ln_bound = 0.f;
+    for (int l = 0; l <= m.L; ++l) vreqs.push_back({m.b[l], m.out[l], &m, 0, l});
+    if (m.ln_g) vreqs.push_back({m.ln_g, m.out[m.L], &m, 1, 0}), vreqs.push_back({m.ln_b, m.out[m.L], &m, 2, 0});
+  };
+  if (p->w_enc) want_mlp(p->enc_node), want_mlp(p->enc_blk_edge), want_mlp(p->enc_blk_node);
+  if (p->w_proc)
+    for (int k = 0; k < d.num_blocks; ++k) want_mlp(p->proc_edge[k]), want_mlp(p->proc_node[k]);
+  if (p->w_dec) want_mlp(p->dec_blk_edge), want_mlp(p->dec_blk_node), want_mlp(p->dec_node_dec);
+  const size_t n = reqs.size(), nv = vreqs.size();
+  GW_TRY(p->tc_absmax.alloc(n + nv));
+  GW_CUDA(cudaMemsetAsync(p->tc_absmax.p, 0, (n + nv) * sizeof(float), st));
   size_t total = 0;
   for (size_t i = 0; i < n; ++i) {
     GW_CUDA(launch_absmax(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, p->tc_absmax.p + i, st));
     total += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
   }
-  std::vector<float> amax(n);
-  GW_CUDA(cudaMemcpyAsync(amax.data(), p->tc_absmax.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  for (size_t i = 0; i < nv; ++i) GW_CUDA(launch_absmax(vreqs[i].v, vreqs[i].n, vreqs[i].n, 1, p->tc_absmax.p + n + i, st));
+  std::vector<float> amax(n + nv);
+  GW_CUDA(cudaMemcpyAsync(amax.data(), p->tc_absmax.p, (n + nv) * sizeof(float), cudaMemcpyDeviceToHost, st));
   GW_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < nv; ++i) {
+    const VReq& r = vreqs[i];
+    const float a = amax[n + i];
+    if (r.what == 0) r.m->bmax[r.l] = a;
+    else if (r.what == 1) r.m->ln_bound += std::sqrt((float)r.n) * a;
+    else r.m->ln_bound += a;
+  }
   if (p->tc_packed.n != total) GW_TRY(p->tc_packed.alloc(total));
   size_t off = 0;
   for (size_t i = 0; i < n; ++i) {
@@ -454,6 +503,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
     reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
     reqs[i].out->n_valid = reqs[i].N;
     reqs[i].out->winv = 1.f / scale;
+    reqs[i].out->gain = (float)reqs[i].K * amax[i];
     off += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
   }
   return 0;
@@ -492,6 +542,10 @@ static int precompute_encoder_constants(gw_plan* p, cudaStream_t st) {
     c.out = p->C1_enc.p, c.ldo = He;
     GW_TRY(run_op(p, c, st));
   }
+  if (is_tc(p)) {
+    GW_TRY(raw_bound(p, SL_EENC, p->e_enc.p, (long long)N * De, st));
+    GW_TRY(raw_bound(p, SL_C1ENC, p->C1_enc.p, (long long)N * He, st));
+  }
   return 0;
 }
 
@@ -527,6 +581,14 @@ static int precompute_constants(gw_plan* p, cudaStream_t st) {
     GW_TRY(run_op(p, c, st));
   }
   if (p->w_enc && p->have_enc) GW_TRY(precompute_encoder_constants(p, st));
+  if (is_tc(p)) {  // magnitude bounds of the constant tensors the chains read (operand range, gw_tc3.cu)
+    if (p->w_enc) GW_TRY(raw_bound(p, SL_XM0, p->xm0.p, (long long)d.n_mesh * Dn, st));
+    if (p->w_enc && p->have_lat) GW_TRY(raw_bound(p, SL_ELAT, p->e_lat.p, (long long)d.n_lat_edges * De, st));
+    if (p->w_dec && p->have_dec) {
+      GW_TRY(raw_bound(p, SL_EDEC, p->e_dec.p, (long long)d.n_dec_edges * De, st));
+      GW_TRY(raw_bound(p, SL_E1DEC, p->E1_dec.p, (long long)d.n_dec_edges * He, st));
+    }
+  }
   return 0;
 }
 
@@ -534,10 +596,11 @@ static int precompute_constants(gw_plan* p, cudaStream_t st) {
 // stages
 // ---------------------------------------------------------------------------------------------------------------
 // Encoder.forward (encoder.py:197-242) for `nb` samples of `features`; writes x_out [nb*H, Dn].
-static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb, cudaStream_t st) {
+static int stage_encoder(gw_plan* p, const float* features, float* x_out, float* x_out_bound, int nb, cudaStream_t st) {
   const gw_dims& d = p->d;
   const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, N = p->n_in_cur, H = d.n_mesh;
   RowSrc none;
+  if (is_tc(p)) GW_CUDA(cudaMemsetAsync(sl(p, SL_FEAT), 0, sizeof(float), st));
   for (int s0 = 0; s0 < nb; s0 += p->chunk) {
     const int cb = std::min(p->chunk, nb - s0);
     const float* f = features + (size_t)s0 * N * d.in_dim;
@@ -553,24 +616,27 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
         ch.K0 = p->tc_enc_node.w0.K;
         if ((d.in_dim & 63) || (reinterpret_cast<uintptr_t>(f) & 15)) {
           // widen the feature rows to K0 (zero padded, 16-byte aligned) so that stage 0 takes the 128-bit path; the
-          // lat/lon row buffer is free here (the whole encoder block runs inside this chain)
+          // lat/lon row buffer is free here (the whole encoder block runs inside this chain).  The same pass takes the
+          // absolute maximum of the raw features: the chain scales its fp16-split operands from it.
           TimedLaunch t(p, st);
-          GW_CUDA(launch_pad_rows(f, d.in_dim, d.in_dim, xg, ch.K0, (long long)cb * N, st));
-          ch.a0[0] = src_stream(xg, ch.K0, ch.K0, N);
+          GW_CUDA(launch_pad_rows(f, d.in_dim, d.in_dim, xg, ch.K0, (long long)cb * N, sl(p, SL_FEAT), st));
+          ch.a0[0] = bounded(src_stream(xg, ch.K0, ch.K0, N), sl(p, SL_FEAT));
         } else {
-          ch.a0[0] = src_stream(f, d.in_dim, d.in_dim, N);
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_absmax_flat(f, (long long)cb * N * d.in_dim, sl(p, SL_FEAT), st));
+          ch.a0[0] = bounded(src_stream(f, d.in_dim, d.in_dim, N), sl(p, SL_FEAT));
         }
         const Mlp &mn = p->enc_node, &me = p->enc_blk_edge;
-        ch.layer[0] = tc_layer(p->tc_enc_node.w0, mn.b[0], true, true);
-        ch.layer[1] = tc_layer(p->tc_enc_node.w1, mn.b[1], true, true);
-        ch.layer[2] = tc_layer(p->tc_enc_node.w2, mn.b[2], false, true);
+        ch.layer[0] = tc_layer(p->tc_enc_node.w0, &mn, 0, true, true);
+        ch.layer[1] = tc_layer(p->tc_enc_node.w1, &mn, 1, true, true);
+        ch.layer[2] = tc_layer(p->tc_enc_node.w2, &mn, 2, false, true);
         tc_ln(ch.layer[2], mn, none);
-        ch.layer[3] = tc_layer(p->tc_enc_edge.w0, nullptr, true, true);
-        ch.layer[3].add[0] = src_bcast(p->C1_enc.p, He, He);
-        ch.layer[4] = tc_layer(p->tc_enc_edge.w1, me.b[1], true, true);
-        ch.layer[5] = tc_layer(p->tc_enc_edge.w2, me.b[2], false, false);
-        tc_ln(ch.layer[5], me, src_bcast(p->e_enc.p, De, De));
-        tc_out(ch.layer[5], eprime, De, De);
+        ch.layer[3] = tc_layer(p->tc_enc_edge.w0, nullptr, -1, true, true);
+        ch.layer[3].add[0] = bounded(src_bcast(p->C1_enc.p, He, He), sl(p, SL_C1ENC));
+        ch.layer[4] = tc_layer(p->tc_enc_edge.w1, &me, 1, true, true);
+        ch.layer[5] = tc_layer(p->tc_enc_edge.w2, &me, 2, false, false);
+        tc_ln(ch.layer[5], me, bounded(src_bcast(p->e_enc.p, De, De), sl(p, SL_EENC)));
+        tc_out(ch.layer[5], eprime, De, De, sl(p, SL_ROWS_E));
         ch.n_layers = 6;
         GW_TRY(run_chain(p, ch, st));
       }
@@ -579,19 +645,19 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, int nb
       {
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = cb;
-        {  // the lat/lon -> mesh segments are very skewed: reduce them with one CTA per (cell, sample) first
+        {  // the lat/lon -> mesh segments are very skewed (a polar cell collects thousands of points): reduced by their own kernel
           TimedLaunch t(p, st);
           GW_CUDA(launch_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->agg_mesh.p, De, st));
         }
-        ch.a0[0] = src_bcast(p->xm0.p, Dn, Dn);
-        ch.a0[1] = src_stream(p->agg_mesh.p, De, De, H);
+        ch.a0[0] = bounded(src_bcast(p->xm0.p, Dn, Dn), sl(p, SL_XM0));
+        ch.a0[1] = bounded(src_stream(p->agg_mesh.p, De, De, H), sl(p, SL_ROWS_E), (float)std::max(p->enc_maxdeg, 1));
         ch.K0 = Dn + De;
         const Mlp& m = p->enc_blk_node;
-        ch.layer[0] = tc_layer(p->tc_enc_mnode.w0, m.b[0], true, true);
-        ch.layer[1] = tc_layer(p->tc_enc_mnode.w1, m.b[1], true, true);
-        ch.layer[2] = tc_layer(p->tc_enc_mnode.w2, m.b[2], false, false);
-        tc_ln(ch.layer[2], m, src_bcast(p->xm0.p, Dn, Dn));
-        tc_out(ch.layer[2], x_out + (size_t)s0 * H * Dn, Dn, Dn);
+        ch.layer[0] = tc_layer(p->tc_enc_mnode.w0, &m, 0, true, true);
+        ch.layer[1] = tc_layer(p->tc_enc_mnode.w1, &m, 1, true, true);
+        ch.layer[2] = tc_layer(p->tc_enc_mnode.w2, &m, 2, false, false);
+        tc_ln(ch.layer[2], m, bounded(src_bcast(p->xm0.p, Dn, Dn), sl(p, SL_XM0)));
+        tc_out(ch.layer[2], x_out + (size_t)s0 * H * Dn, Dn, Dn, x_out_bound);
         ch.n_layers = 3;
         GW_TRY(run_chain(p, ch, st));
       }
@@ -631,8 +697,11 @@ struct ProcGraph {
   const int32_t *src, *dst, *ptr;
   const float* e0;
   bool e0_broadcast;
+  int maxdeg, mindeg;    // longest / shortest per-node segment of incoming edges
+  const float* e0_bound; // magnitude bound of e0
 };
-static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, float* x_out, int nb, cudaStream_t st) {
+static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, float* x_out, int x_in_slot, int x_out_slot, int nb,
+                           cudaStream_t st) {
   const gw_dims& d = p->d;
   const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = g.H, El = g.El;
   const float* x_cur = x_in;
@@ -640,73 +709,89 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
   float* eb[2] = {p->ebuf0.p, p->ebuf1.p};
   const float* e_cur = nullptr;  // null: block 0 reads e0
   bool p_ready = false;          // P of the coming block was produced by the previous block's node chain
+  auto xs = [&](const float* buf) { return sl(p, buf == xb[0] ? SL_X0 : (buf == xb[1] ? SL_X1 : (buf == x_in ? x_in_slot : x_out_slot))); };
+  auto es = [&](const float* buf) { return sl(p, buf == eb[0] ? SL_E0 : SL_E1); };
+  // the per-node sums of e' are produced by the edge chain itself when every node collects at most 8 edges (icosahedral
+  // meshes: 6 or 7); longer segments (arbitrary caller graphs) keep the separate reduction kernel
+  const bool fuse = is_tc(p) && p->fuse_seg && g.maxdeg >= 1 && g.maxdeg <= 8;
   for (int k = 0; k < d.num_blocks; ++k) {
     const Mlp& me = p->proc_edge[k];
     const Mlp& mn = p->proc_node[k];
     if (is_tc(p)) {
+      const bool last = k == d.num_blocks - 1;
       float* e_next = eb[k & 1];
-      float* x_next = (k == d.num_blocks - 1) ? x_out : xb[k & 1];
+      float* x_next = last ? x_out : xb[k & 1];
       if (x_next == x_cur) x_next = xb[(k & 1) ^ 1];
-      const RowSrc e_src = e_cur ? src_stream(e_cur, De, De, El)
-                                 : (g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El));
+      const RowSrc e_src = e_cur ? bounded(src_stream(e_cur, De, De, El), es(e_cur))
+                                 : bounded(g.e0_broadcast ? src_bcast(g.e0, De, De) : src_stream(g.e0, De, De, El), g.e0_bound);
       if (!p_ready) {  // P = x [W1s ; W1d]^T : two products of the same operand (block 0; later blocks: see the node chain)
         p->cur_tag = TAG_PROC_P;
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
-        ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
+        ch.a0[0] = bounded(src_stream(x_cur, Dn, Dn, H), xs(x_cur));
         ch.K0 = Dn;
-        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0, nullptr, false, false);
-        tc_out(ch.layer[0], p->P.p, 2 * He, He);
-        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w0b, nullptr, false, false);
+        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0, nullptr, -1, false, false);
+        tc_out(ch.layer[0], p->P.p, 2 * He, He, sl(p, SL_P));
+        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w0b, nullptr, -1, false, false);
         ch.layer[1].reuse_a = 1;
-        tc_out(ch.layer[1], p->P.p + He, 2 * He, He);
+        tc_out(ch.layer[1], p->P.p + He, 2 * He, He, sl(p, SL_P));
         ch.n_layers = 2;
         GW_TRY(run_chain(p, ch, st));
       }
       p->cur_tag = TAG_PROC_EDGE;
-      {  // e' = LN(W3 relu(W2 relu(W1e e + b1 + P_s[src] + P_d[dst]) + b2) + b3) + e
+      {  // e' = LN(W3 relu(W2 relu(W1e e + b1 + P_s[src] + P_d[dst]) + b2) + b3) + e   (+ per-node sums of e' when fused)
         TcChain ch;
         ch.rows_per_sample = El, ch.batch = nb;
         ch.a0[0] = e_src;
         ch.K0 = De;
-        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0c, me.b[0], true, true);
-        ch.layer[0].add[0] = src_gather(p->P.p, 2 * He, He, g.src, H, 0);
-        ch.layer[0].add[1] = src_gather(p->P.p, 2 * He, He, g.dst, H, He);
-        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w1, me.b[1], true, true);
-        ch.layer[2] = tc_layer(p->tc_proc_edge[k].w2, me.b[2], false, false);
+        ch.layer[0] = tc_layer(p->tc_proc_edge[k].w0c, &me, 0, true, true);
+        ch.layer[0].add[0] = bounded(src_gather(p->P.p, 2 * He, He, g.src, H, 0), sl(p, SL_P));
+        ch.layer[0].add[1] = bounded(src_gather(p->P.p, 2 * He, He, g.dst, H, He), sl(p, SL_P));
+        ch.layer[1] = tc_layer(p->tc_proc_edge[k].w1, &me, 1, true, true);
+        ch.layer[2] = tc_layer(p->tc_proc_edge[k].w2, &me, 2, false, false);
         tc_ln(ch.layer[2], me, e_src);
-        tc_out(ch.layer[2], e_next, De, De);
+        if (!(fuse && last)) tc_out(ch.layer[2], e_next, De, De, es(e_next));  // (the last block's e' is only ever summed)
+        if (fuse) {
+          TcLayer& L = ch.layer[2];
+          L.seg_dst = g.dst, L.seg_out = p->agg_mesh.p, L.seg_ld = De, L.seg_rows = H, L.seg_carry = p->seg_carry.p;
+          L.seg_maxdeg = (float)g.maxdeg, L.seg_bound = sl(p, SL_AGG_MESH);
+          if (g.mindeg == 0) GW_CUDA(cudaMemsetAsync(p->agg_mesh.p, 0, (size_t)nb * H * De * sizeof(float), st));  // nodes without edges
+        }
         ch.n_layers = 3;
         GW_TRY(run_chain(p, ch, st));
+        if (fuse) {
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_seg_carry(p->seg_carry.p, g.dst, El, H, nb, p->agg_mesh.p, De, st));
+        }
       }
       p->cur_tag = TAG_PROC_NODE;
       {  // x' = LN(MLP([x ; sum_in e'])) + x
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
-        {  // per-node sum of incoming e' rows (contiguous CSR segments of <= 7 rows): coalesced reduction kernel, so the
-           // chain reads two plain row streams
+        if (!fuse) {  // per-node sum of incoming e' rows (contiguous CSR segments): coalesced reduction kernel
           TimedLaunch t(p, st);
           GW_CUDA(launch_segsum(e_next, De, De, g.ptr, nullptr, El, H, nb, p->agg_mesh.p, De, st));
         }
-        ch.a0[0] = src_stream(x_cur, Dn, Dn, H);
-        ch.a0[1] = src_stream(p->agg_mesh.p, De, De, H);
+        ch.a0[0] = bounded(src_stream(x_cur, Dn, Dn, H), xs(x_cur));
+        ch.a0[1] = fuse ? bounded(src_stream(p->agg_mesh.p, De, De, H), sl(p, SL_AGG_MESH))
+                        : bounded(src_stream(p->agg_mesh.p, De, De, H), es(e_next), (float)std::max(g.maxdeg, 1));
         ch.K0 = Dn + De;
-        ch.layer[0] = tc_layer(p->tc_proc_node[k].w0, mn.b[0], true, true);
-        ch.layer[1] = tc_layer(p->tc_proc_node[k].w1, mn.b[1], true, true);
-        ch.layer[2] = tc_layer(p->tc_proc_node[k].w2, mn.b[2], false, false);
-        tc_ln(ch.layer[2], mn, src_stream(x_cur, Dn, Dn, H));
-        tc_out(ch.layer[2], x_next, Dn, Dn);
+        ch.layer[0] = tc_layer(p->tc_proc_node[k].w0, &mn, 0, true, true);
+        ch.layer[1] = tc_layer(p->tc_proc_node[k].w1, &mn, 1, true, true);
+        ch.layer[2] = tc_layer(p->tc_proc_node[k].w2, &mn, 2, false, false);
+        tc_ln(ch.layer[2], mn, bounded(src_stream(x_cur, Dn, Dn, H), xs(x_cur)));
+        tc_out(ch.layer[2], x_next, Dn, Dn, xs(x_next));
         ch.n_layers = 3;
         p_ready = false;
         if (k + 1 < d.num_blocks && He == Dn) {
           // the next block's P = x' [W1s ; W1d]^T needs exactly the rows this chain has just produced: two more products
           // of the same operand, and the separate P launches (and their re-read of x') disappear
           ch.layer[2].feeds_next = 1;
-          ch.layer[3] = tc_layer(p->tc_proc_edge[k + 1].w0, nullptr, false, false);
-          tc_out(ch.layer[3], p->P.p, 2 * He, He);
-          ch.layer[4] = tc_layer(p->tc_proc_edge[k + 1].w0b, nullptr, false, false);
+          ch.layer[3] = tc_layer(p->tc_proc_edge[k + 1].w0, nullptr, -1, false, false);
+          tc_out(ch.layer[3], p->P.p, 2 * He, He, sl(p, SL_P));
+          ch.layer[4] = tc_layer(p->tc_proc_edge[k + 1].w0b, nullptr, -1, false, false);
           ch.layer[4].reuse_a = 1;
-          tc_out(ch.layer[4], p->P.p + He, 2 * He, He);
+          tc_out(ch.layer[4], p->P.p + He, 2 * He, He, sl(p, SL_P));
           ch.n_layers = 5;
           p_ready = true;
         }
@@ -751,14 +836,25 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
   return 0;
 }
 static ProcGraph latent_graph_of(gw_plan* p) {
-  return ProcGraph{p->d.n_mesh, p->d.n_lat_edges, p->lat_src.p, p->lat_dst.p, p->lat_ptr.p, p->e_lat.p, true};
+  return ProcGraph{p->d.n_mesh, p->d.n_lat_edges, p->lat_src.p, p->lat_dst.p, p->lat_ptr.p, p->e_lat.p, true,
+                   p->lat_maxdeg, p->lat_mindeg, sl(p, SL_ELAT)};
 }
 
 // AssimilatorDecoder.forward (assimilator_decoder.py:173-200) + Decoder residual (decoder.py:92-94).
-static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int start_ld, float* out, int nb, cudaStream_t st) {
+// e' rows of the decoder block are only materialised by the CUDA-core path and by the unfused fallback: allocated on demand
+static int ensure_rows_e(gw_plan* p, size_t floats) {
+  if (p->rows_e.n >= floats) return 0;
+  GW_CUDA(cudaDeviceSynchronize());
+  return p->rows_e.alloc(floats);
+}
+
+static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const float* start, int start_ld, float* out, int nb,
+                         cudaStream_t st) {
   const gw_dims& d = p->d;
   const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = d.n_mesh, Ed = d.n_dec_edges, No = d.n_out;
   RowSrc none;
+  const bool fuse = is_tc(p) && p->fuse_seg && p->dec_maxdeg >= 1 && p->dec_maxdeg <= 8;
+  if (!fuse) GW_TRY(ensure_rows_e(p, (size_t)p->chunk * std::max((size_t)p->d.n_in, (size_t)Ed) * De));
   for (int s0 = 0; s0 < nb; s0 += p->chunk) {
     const int cb = std::min(p->chunk, nb - s0);
     const float* x = x_in + (size_t)s0 * H * Dn;
@@ -772,58 +868,72 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
       {
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = cb;
-        ch.a0[0] = src_stream(x, Dn, Dn, H);
+        ch.a0[0] = bounded(src_stream(x, Dn, Dn, H), sl(p, x_in_slot));
         ch.K0 = Dn;
-        ch.layer[0] = tc_layer(p->tc_dec_edge.w0, nullptr, false, false);
-        tc_out(ch.layer[0], Pd, He, He);
+        ch.layer[0] = tc_layer(p->tc_dec_edge.w0, nullptr, -1, false, false);
+        tc_out(ch.layer[0], Pd, He, He, sl(p, SL_P));
         ch.n_layers = 1;
         GW_TRY(run_chain(p, ch, st));
       }
       p->cur_tag = TAG_DEC_EDGE;
-      {  // layer 1 = relu(Pd[src] + E1) is the operand assembly; layers 2, 3 + LN + e_dec residual on the tensor cores
+      {  // layer 1 = relu(Pd[src] + E1) is the operand assembly; layers 2, 3 + LN + e_dec residual on the tensor cores; the rows
+         // are summed per lat/lon point in the epilogue (fused): e' is never written (the reference discards it too: `out, _ =`)
         TcChain ch;
         ch.rows_per_sample = Ed, ch.batch = cb;
-        ch.a0[0] = src_gather_bcast_relu(Pd, He, He, p->dec_src.p, H, p->E1_dec.p, He);
+        ch.a0[0] = bounded(src_gather_bcast_relu(Pd, He, He, p->dec_src.p, H, p->E1_dec.p, He), sl(p, SL_P));
+        ch.a0[0].bound2 = sl(p, SL_E1DEC);
         ch.K0 = He;
-        ch.layer[0] = tc_layer(p->tc_dec_edge.w1, me.b[1], true, true);
-        ch.layer[1] = tc_layer(p->tc_dec_edge.w2, me.b[2], false, false);
-        tc_ln(ch.layer[1], me, src_bcast(p->e_dec.p, De, De));
-        tc_out(ch.layer[1], eprime, De, De);
+        ch.layer[0] = tc_layer(p->tc_dec_edge.w1, &me, 1, true, true);
+        ch.layer[1] = tc_layer(p->tc_dec_edge.w2, &me, 2, false, false);
+        tc_ln(ch.layer[1], me, bounded(src_bcast(p->e_dec.p, De, De), sl(p, SL_EDEC)));
+        if (fuse) {
+          TcLayer& L = ch.layer[1];
+          L.seg_dst = p->dec_dst.p, L.seg_out = p->agg_grid.p, L.seg_ld = De, L.seg_rows = No, L.seg_carry = p->seg_carry.p;
+          L.seg_maxdeg = (float)p->dec_maxdeg, L.seg_bound = sl(p, SL_AGG_GRID);
+          if (p->dec_mindeg == 0) GW_CUDA(cudaMemsetAsync(p->agg_grid.p, 0, (size_t)cb * No * De * sizeof(float), st));
+        } else {
+          tc_out(ch.layer[1], eprime, De, De, sl(p, SL_ROWS_E));
+        }
         ch.n_layers = 2;
         GW_TRY(run_chain(p, ch, st));
+        if (fuse) {
+          TimedLaunch t(p, st);
+          GW_CUDA(launch_seg_carry(p->seg_carry.p, p->dec_dst.p, Ed, No, cb, p->agg_grid.p, De, st));
+        }
       }
       p->cur_tag = TAG_DEC_NODE;
       {  // lat/lon node update (x == 0, so only the aggregate half of W1 and no residual)
         TcChain ch;
         ch.rows_per_sample = No, ch.batch = cb;
-        {
+        if (!fuse) {
           TimedLaunch t(p, st);
           GW_CUDA(launch_segsum(eprime, De, De, p->dec_ptr.p, nullptr, Ed, No, cb, p->agg_grid.p, De, st));
         }
-        ch.a0[0] = src_stream(p->agg_grid.p, De, De, No);
+        ch.a0[0] = fuse ? bounded(src_stream(p->agg_grid.p, De, De, No), sl(p, SL_AGG_GRID))
+                        : bounded(src_stream(p->agg_grid.p, De, De, No), sl(p, SL_ROWS_E), (float)std::max(p->dec_maxdeg, 1));
         ch.K0 = De;
-        ch.layer[0] = tc_layer(p->tc_dec_node.w0, mn.b[0], true, true);
-        ch.layer[1] = tc_layer(p->tc_dec_node.w1, mn.b[1], true, true);
-        ch.layer[2] = tc_layer(p->tc_dec_node.w2, mn.b[2], false, false);
+        ch.layer[0] = tc_layer(p->tc_dec_node.w0, &mn, 0, true, true);
+        ch.layer[1] = tc_layer(p->tc_dec_node.w1, &mn, 1, true, true);
+        ch.layer[2] = tc_layer(p->tc_dec_node.w2, &mn, 2, false, false);
         tc_ln(ch.layer[2], mn, none);
         if (p->tc_dec_out_ok) {  // node_decoder (256->128->128->out, no norm) + start-feature residual in the same chain
           const Mlp& m = p->dec_node_dec;
           ch.layer[2].feeds_next = 1;
-          ch.layer[3] = tc_layer(p->tc_dec_out.w0, m.b[0], true, true);
-          ch.layer[4] = tc_layer(p->tc_dec_out.w1, m.b[1], true, true);
+          ch.layer[3] = tc_layer(p->tc_dec_out.w0, &m, 0, true, true);
+          ch.layer[4] = tc_layer(p->tc_dec_out.w1, &m, 1, true, true);
           if (p->tc_dec_out.w1.N <= Dn && !(p->tc_dec_out.w1.N & 63)) {
             // the narrow output layer (78 of 80 columns, 8-byte aligned rows) would take the whole chain off the lean
             // path: run it as a chain of its own on the hidden rows h
             ch.layer[4].feeds_next = 0;
             const int Hd = p->tc_dec_out.w1.N;
-            tc_out(ch.layer[4], xg, Hd, Hd);
+            tc_out(ch.layer[4], xg, Hd, Hd, sl(p, SL_ROWS_N));
             ch.n_layers = 5;
             GW_TRY(run_chain(p, ch, st));
             TcChain c2;
             c2.rows_per_sample = No, c2.batch = cb;
-            c2.a0[0] = src_stream(xg, Hd, Hd, No);
+            c2.a0[0] = bounded(src_stream(xg, Hd, Hd, No), sl(p, SL_ROWS_N));
             c2.K0 = Hd;
-            c2.layer[0] = tc_layer(p->tc_dec_out.w2, m.b[2], false, false);
+            c2.layer[0] = tc_layer(p->tc_dec_out.w2, &m, 2, false, false);
             if (start && d.residual_dim > 0)
               c2.layer[0].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
             tc_out(c2.layer[0], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
@@ -831,7 +941,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
             GW_TRY(run_chain(p, c2, st));
             continue;
           }
-          ch.layer[5] = tc_layer(p->tc_dec_out.w2, m.b[2], false, false);
+          ch.layer[5] = tc_layer(p->tc_dec_out.w2, &m, 2, false, false);
           if (start && d.residual_dim > 0)
             ch.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
           tc_out(ch.layer[5], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
@@ -839,16 +949,17 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
           GW_TRY(run_chain(p, ch, st));
           continue;
         }
-        tc_out(ch.layer[2], xg, Dn, Dn);
+        tc_out(ch.layer[2], xg, Dn, Dn, sl(p, SL_ROWS_N));
         ch.n_layers = 3;
         GW_TRY(run_chain(p, ch, st));
       }
-      {  // node_decoder on the CUDA cores when its shape does not fit the chain kernel
+      for (int b = 0; b < cb; ++b) {  // node_decoder on the CUDA cores when its shape does not fit the chain kernel (sample by
+                                      // sample: the tensor-core plan's ping-pong scratch holds one sample)
         const Mlp& m = p->dec_node_dec;
-        GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
+        GemmOp fo = first_op(No, 1, src_stream(xg + (size_t)b * No * Dn, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
         RowSrc res;
-        if (start && d.residual_dim > 0) res = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
-        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * d.out_dim, d.out_dim, st));
+        if (start && d.residual_dim > 0) res = src_stream(start + (size_t)(s0 + b) * No * start_ld, start_ld, d.out_dim, No);
+        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)(s0 + b) * No * d.out_dim, d.out_dim, st));
       }
       continue;
     }
@@ -883,6 +994,18 @@ static int stage_decoder(gw_plan* p, const float* x_in, const float* start, int 
       GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * d.out_dim, d.out_dim, st));
     }
   }
+  return 0;
+}
+
+// longest / shortest segment of a CSR (and, optionally, the target of every entry); synchronises `st` (graph upload time)
+static int csr_stats(gw_plan* p, const int32_t* ptr, int n, int32_t* dst, int* maxdeg, int* mindeg, cudaStream_t st) {
+  const int init[2] = {0, 0x7fffffff};
+  int got[2] = {0, 0};
+  GW_CUDA(cudaMemcpyAsync(p->deg_stats.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  GW_CUDA(launch_csr_expand(ptr, n, dst, p->deg_stats.p, st));
+  GW_CUDA(cudaMemcpyAsync(got, p->deg_stats.p, sizeof(got), cudaMemcpyDeviceToHost, st));
+  GW_CUDA(cudaStreamSynchronize(st));
+  *maxdeg = got[0], *mindeg = n > 0 ? got[1] : 0;
   return 0;
 }
 
@@ -952,15 +1075,21 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   const size_t Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, Hn = d.hidden_node;
   const size_t max_hid = std::max({Dn, De, He, Hn, (size_t)d.hidden_dec, (size_t)d.out_dim});
   const size_t max_rows = std::max({(size_t)d.n_in, (size_t)d.n_out, (size_t)d.n_mesh, (size_t)d.n_lat_edges, (size_t)d.n_dec_edges});
-  // chunking: keep the per-pass scratch of the lat/lon-sized stages under ~48 GB
-  const size_t per_sample = (2 * max_rows * max_hid + std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De +
-                             std::max((size_t)d.n_in, (size_t)d.n_out) * Dn) * sizeof(float);
+  // chunking: keep the per-pass scratch of the lat/lon-sized stages under ~48 GB.  The tensor-core path never writes the
+  // decoder's e' rows (their per-point sums are formed in the edge chain's epilogue), and its hidden activations stay on
+  // the SM, so its per-sample scratch is three lat/lon-sized row buffers; the CUDA-core path also needs e' and the ping-pong.
+  const bool tc = d.precision != GW_PREC_FP32_SIMT;
+  const size_t n_io = std::max((size_t)d.n_in, (size_t)d.n_out);
+  const size_t dec_tiles = ((size_t)d.n_dec_edges + 127) / 128, lat_tiles = ((size_t)d.n_lat_edges + 127) / 128;
+  const size_t per_sample = tc ? (n_io * Dn + (size_t)d.n_in * De + (size_t)d.n_out * De + dec_tiles * 1024) * sizeof(float)
+                               : (2 * max_rows * max_hid + std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De + n_io * Dn) * sizeof(float);
   size_t chunk = std::max<size_t>(1, std::min<size_t>(d.max_batch, (48ull << 30) / std::max<size_t>(per_sample, 1)));
   if (const char* force = getenv("GW_B200_CHUNK")) {  // test knob: exercise the chunked stage loops on small grids
     const long v = atol(force);
     if (v >= 1) chunk = std::min<size_t>((size_t)v, (size_t)d.max_batch);
   }
   p->chunk = (int)chunk;
+  p->fuse_seg = tc && !getenv("GW_TC3_NOSEG");  // diagnostics: GW_TC3_NOSEG=1 keeps the separate segment-sum kernels
   const size_t B = d.max_batch;
   int rc = 0;
   rc |= p->enc_mesh.alloc(d.n_in) | p->enc_perm.alloc(d.n_in) | p->enc_ptr.alloc(d.n_mesh + 1);
@@ -968,22 +1097,27 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->lat_src.alloc(d.n_lat_edges) | p->lat_dst.alloc(d.n_lat_edges) | p->lat_ptr.alloc(d.n_mesh + 1);
   rc |= p->lat_attr.alloc((size_t)d.n_lat_edges * 2);
   rc |= p->dec_src.alloc(d.n_dec_edges) | p->dec_ptr.alloc(d.n_out + 1) | p->dec_attr.alloc((size_t)d.n_dec_edges * 2);
+  rc |= p->dec_dst.alloc(d.n_dec_edges) | p->deg_stats.alloc(2) | p->bounds.alloc(gw::SL_COUNT);
   rc |= p->zeros_h3.alloc((size_t)d.n_mesh * d.in_dim);
   rc |= p->e_enc.alloc((size_t)d.n_in * De) | p->xm0.alloc((size_t)d.n_mesh * Dn) | p->C1_enc.alloc((size_t)d.n_in * He);
   rc |= p->e_lat.alloc((size_t)d.n_lat_edges * De) | p->e_dec.alloc((size_t)d.n_dec_edges * De);
   rc |= p->E1_dec.alloc((size_t)d.n_dec_edges * He) | p->tmpP.alloc((size_t)d.n_mesh * He);
-  rc |= p->bufA.alloc(chunk * max_rows * max_hid) | p->bufB.alloc(chunk * max_rows * max_hid);
-  // bufA/bufB are also used for full-batch processor passes over n_lat_edges rows
-  if (!rc && B * std::max((size_t)d.n_lat_edges, (size_t)d.n_mesh) > chunk * max_rows) {
-    rc |= p->bufA.alloc(B * max_rows * max_hid) | p->bufB.alloc(B * max_rows * max_hid);
+  {  // hidden-activation ping-pong of run_mlp: every stage on the CUDA-core path, the one-off constant precompute
+     // (one sample's worth of rows) on the tensor-core path
+    size_t pp = (tc ? 1 : chunk) * max_rows * max_hid;
+    if (!tc && B * std::max((size_t)d.n_lat_edges, (size_t)d.n_mesh) > chunk * max_rows) pp = B * max_rows * max_hid;
+    rc |= p->bufA.alloc(pp) | p->bufB.alloc(pp);
   }
-  rc |= p->rows_n.alloc(chunk * std::max((size_t)d.n_in, (size_t)d.n_out) * Dn);
-  rc |= p->rows_e.alloc(chunk * std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De);
+  rc |= p->rows_n.alloc(chunk * n_io * Dn);
+  rc |= p->rows_e.alloc(chunk * (tc ? (size_t)d.n_in : std::max((size_t)d.n_in, (size_t)d.n_dec_edges)) * De);
   rc |= p->xbuf0.alloc(B * d.n_mesh * Dn) | p->xbuf1.alloc(B * d.n_mesh * Dn);
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
   rc |= p->agg_mesh.alloc(B * d.n_mesh * De);
-  if (d.precision != GW_PREC_FP32_SIMT) rc |= p->agg_grid.alloc(chunk * d.n_out * De);
+  if (tc) {
+    rc |= p->agg_grid.alloc(chunk * d.n_out * De);
+    rc |= p->seg_carry.alloc(std::max(chunk * dec_tiles, B * (lat_tiles + 1)) * 1024);
+  }
   if (rc) {
     std::string keep = gw::g_err;
     gw_plan_destroy(p);
@@ -991,6 +1125,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
     return 1;
   }
   GW_CUDA_P(cudaMemset(p->zeros_h3.p, 0, p->zeros_h3.bytes()));
+  GW_CUDA_P(cudaMemset(p->bounds.p, 0, p->bounds.bytes()));
   GW_CUDA_P(cudaHostAlloc((void**)&p->tc_status_host, 64 * sizeof(int32_t), cudaHostAllocMapped));
   std::memset(p->tc_status_host, 0, 64 * sizeof(int32_t));
   GW_CUDA_P(cudaHostGetDevicePointer((void**)&p->tc_status_dev, p->tc_status_host, 0));
@@ -1009,6 +1144,7 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
   p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release(), p->agg_grid.release();
+  p->bounds.release(), p->dec_dst.release(), p->seg_carry.release(), p->deg_stats.release();
   if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1024,6 +1160,7 @@ int64_t gw_plan_device_bytes(const gw_plan* p) {
                                  &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e,
                                  &p->xbuf0, &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     t += b->bytes();
+  t += p->tc_packed.bytes() + p->agg_mesh.bytes() + p->agg_grid.bytes() + p->seg_carry.bytes() + p->dec_dst.bytes();
   return (int64_t)t;
 }
 
@@ -1039,6 +1176,10 @@ int gw_plan_set_encoder_graph(gw_plan* p, int32_t n_in, const int32_t* enc_mesh,
   GW_CUDA(cudaMemcpyAsync(p->enc_attr.p, attr, (size_t)n_in * p->d.enc_edge_attr_dim * 4, cudaMemcpyDeviceToDevice, st));
   p->n_in_cur = n_in;
   p->have_enc = true;
+  {
+    int mn = 0;
+    GW_TRY(gw::csr_stats(p, p->enc_ptr.p, p->d.n_mesh, nullptr, &p->enc_maxdeg, &mn, st));
+  }
   if (p->w_enc) GW_TRY(gw::precompute_encoder_constants(p, st));  // per-call graphs (assimilator_encoder.py:118)
   return 0;
 }
@@ -1052,6 +1193,7 @@ int gw_plan_set_latent_graph(gw_plan* p, const int32_t* src, const int32_t* dst,
   GW_CUDA(cudaMemcpyAsync(p->lat_dst.p, dst, El * 4, cudaMemcpyDeviceToDevice, st));
   GW_CUDA(cudaMemcpyAsync(p->lat_ptr.p, ptr, (size_t)(p->d.n_mesh + 1) * 4, cudaMemcpyDeviceToDevice, st));
   GW_CUDA(cudaMemcpyAsync(p->lat_attr.p, attr, El * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  GW_TRY(gw::csr_stats(p, p->lat_ptr.p, p->d.n_mesh, nullptr, &p->lat_maxdeg, &p->lat_mindeg, st));
   p->have_lat = true;
   p->w_enc = p->w_proc = p->w_dec = false;  // constants depend on the graphs: weights must be (re)uploaded after
   return 0;
@@ -1065,6 +1207,7 @@ int gw_plan_set_decoder_graph(gw_plan* p, const int32_t* src, const int32_t* ptr
   GW_CUDA(cudaMemcpyAsync(p->dec_src.p, src, Ed * 4, cudaMemcpyDeviceToDevice, st));
   GW_CUDA(cudaMemcpyAsync(p->dec_ptr.p, ptr, (size_t)(p->d.n_out + 1) * 4, cudaMemcpyDeviceToDevice, st));
   GW_CUDA(cudaMemcpyAsync(p->dec_attr.p, attr, Ed * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  GW_TRY(gw::csr_stats(p, p->dec_ptr.p, p->d.n_out, p->dec_dst.p, &p->dec_maxdeg, &p->dec_mindeg, st));
   p->have_dec = true;
   p->w_enc = p->w_proc = p->w_dec = false;
   return 0;
@@ -1097,7 +1240,7 @@ int gw_plan_set_weights(gw_plan* p, const gw_param* params, int32_t n, void* str
 int gw_encoder_forward(gw_plan* p, const float* features, float* x_out, int32_t batch, void* stream) {
   GW_TRY(gw::check_ready(p, batch, gw::NEED_ENC));
   GW_CHECK(features && x_out, "null argument");
-  return gw::stage_encoder(p, features, x_out, batch, (cudaStream_t)stream);
+  return gw::stage_encoder(p, features, x_out, gw::sl(p, gw::SL_XOUT), batch, (cudaStream_t)stream);
 }
 
 int gw_processor_forward(gw_plan* p, const float* x_in, float* x_out, int32_t batch, void* stream) {
@@ -1105,7 +1248,9 @@ int gw_processor_forward(gw_plan* p, const float* x_in, float* x_out, int32_t ba
   GW_CHECK(x_in && x_out, "null argument");
   GW_CHECK(p->have_lat && p->w_enc, "gw_processor_forward uses the plan's latent graph and encoded latent edges; "
                                     "use gw_processor_forward_graph for caller-supplied graphs");
-  return gw::stage_processor(p, gw::latent_graph_of(p), x_in, x_out, batch, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gw::is_tc(p)) GW_TRY(gw::raw_bound(p, gw::SL_XIN, x_in, (long long)batch * p->d.n_mesh * p->d.node_dim, st));
+  return gw::stage_processor(p, gw::latent_graph_of(p), x_in, x_out, gw::SL_XIN, gw::SL_XOUT, batch, st);
 }
 
 int gw_processor_forward_graph(gw_plan* p, const float* x_in, float* x_out, const float* edge_attr, int32_t n_nodes,
@@ -1114,15 +1259,23 @@ int gw_processor_forward_graph(gw_plan* p, const float* x_in, float* x_out, cons
   GW_CHECK(x_in && x_out && edge_attr && src && dst && ptr, "null argument");
   GW_CHECK(n_nodes >= 1 && (size_t)n_nodes <= (size_t)p->d.max_batch * p->d.n_mesh, "n_nodes exceeds max_batch*n_mesh");
   GW_CHECK(n_edges >= 1 && (size_t)n_edges <= (size_t)p->d.max_batch * p->d.n_lat_edges, "n_edges exceeds max_batch*n_lat_edges");
-  gw::ProcGraph g{n_nodes, n_edges, src, dst, ptr, edge_attr, false};
-  return gw::stage_processor(p, g, x_in, x_out, 1, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  gw::ProcGraph g{n_nodes, n_edges, src, dst, ptr, edge_attr, false, 0, 0, gw::sl(p, gw::SL_EIN)};
+  if (gw::is_tc(p)) {
+    GW_TRY(gw::csr_stats(p, ptr, n_nodes, nullptr, &g.maxdeg, &g.mindeg, st));  // decides whether the per-node sums can be fused
+    GW_TRY(gw::raw_bound(p, gw::SL_XIN, x_in, (long long)n_nodes * p->d.node_dim, st));
+    GW_TRY(gw::raw_bound(p, gw::SL_EIN, edge_attr, (long long)n_edges * p->d.edge_dim, st));
+  }
+  return gw::stage_processor(p, g, x_in, x_out, gw::SL_XIN, gw::SL_XOUT, 1, st);
 }
 
 int gw_decoder_forward(gw_plan* p, const float* x_in, const float* start, int32_t start_ld, float* out, int32_t batch, void* stream) {
   GW_TRY(gw::check_ready(p, batch, gw::NEED_DEC));
   GW_CHECK(x_in && out, "null argument");
   GW_CHECK(p->d.residual_dim == 0 || (start && start_ld >= p->d.residual_dim), "start features required (decoder.py:93)");
-  return gw::stage_decoder(p, x_in, start, start_ld, out, batch, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gw::is_tc(p)) GW_TRY(gw::raw_bound(p, gw::SL_XIN, x_in, (long long)batch * p->d.n_mesh * p->d.node_dim, st));
+  return gw::stage_decoder(p, x_in, gw::SL_XIN, start, start_ld, out, batch, st);
 }
 
 int gw_forward(gw_plan* p, const float* features, float* out, int32_t batch, void* stream) {
@@ -1130,9 +1283,9 @@ int gw_forward(gw_plan* p, const float* features, float* out, int32_t batch, voi
   GW_CHECK(features && out, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   // x lives in xbuf0 between stages
-  GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, batch, st));
-  GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, batch, st));
-  return gw::stage_decoder(p, p->xbuf0.p, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, batch, st);
+  GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, gw::sl(p, gw::SL_X0), batch, st));
+  GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, gw::SL_X0, gw::SL_X0, batch, st));
+  return gw::stage_decoder(p, p->xbuf0.p, gw::SL_X0, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, batch, st);
 }
 
 int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {

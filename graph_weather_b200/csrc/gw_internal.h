@@ -14,7 +14,11 @@ void set_error(const std::string& msg);
 // exact-fp32 CUDA-core execution of one row op (gw_simt.cu)
 cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream);
 
-cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, cudaStream_t stream);
+cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, float* amax, cudaStream_t stream);
+cudaError_t launch_absmax_flat(const float* p, long long n, float* amax, cudaStream_t stream);
+cudaError_t launch_csr_expand(const int32_t* ptr, int n, int32_t* dst, int* stats, cudaStream_t stream);
+cudaError_t launch_seg_carry(const float* carry, const int32_t* seg_dst, int rows, int seg_rows, int batch, float* out, int ldo,
+                             cudaStream_t stream);
 cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* ptr, const int32_t* perm, int src_rows,
                           int rows, int batch, float* out, int ldo, cudaStream_t stream);
 

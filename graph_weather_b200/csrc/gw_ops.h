@@ -33,6 +33,10 @@ struct RowSrc {
   const int32_t* idx = nullptr;   // [rows_per_sample]
   const int32_t* ptr = nullptr;   // [rows_per_sample+1]
   const int32_t* perm = nullptr;  // optional edge permutation for SEGSUM
+  const float* bound2 = nullptr;  // SRC_GATHER_BCAST_RELU: bound of base2
+  float bound_mul = 1.f;          // the source's values are bounded by *bound * bound_mul (e.g. sums of up to bound_mul rows)
+  const float* bound = nullptr;   // device float: |values of this source| <= *bound (null: unknown).  Tensor-core chains use it
+                                  // to scale fp16-split operands into range (gw_tc3.cu, "operand range")
 };
 
 struct GemmOp {
@@ -72,6 +76,20 @@ struct TcLayer {
   int32_t feeds_next = 0;     // result becomes the A operand of the next layer
   int32_t reuse_a = 0;        // this layer multiplies the same A operand as the previous layer
   int32_t kind = -1;          // gw_tc3 launcher: epilogue feature mask if a specialised instance exists, else -1 (flags read at run time)
+  // operand range (gw_tc3.cu): a rigorous magnitude bound travels with every tensor so that each fp16-split operand can be
+  // scaled by a power of two into the fp16 range.  |A . W^T| <= gain * max|A| with gain = K * max|W|; off = max|bias|.
+  float gain = 0.f, off = 0.f;
+  float ln_bound = 0.f;       // LayerNorm layers: sqrt(N) * max|gamma| + max|beta| bounds the normalised row
+  float* out_bound = nullptr; // device float the kernel sets to the bound of this layer's result (CTA 0), for `out` consumers
+  // fused per-target sum of the result rows (graph_net_block.py:188 scatter_sum): rows are grouped by target (seg_dst
+  // non-decreasing, segments of <= 8 rows); each complete segment sum goes to seg_out, pieces cut by a 32-row quadrant
+  // boundary go to seg_carry and are added by gw_seg_carry_kernel.
+  const int32_t* seg_dst = nullptr;  // [rows_per_sample] target of every row
+  float* seg_out = nullptr;          // [(b * seg_rows + target) * seg_ld + n]
+  float* seg_carry = nullptr;        // [((b * tiles_per_sample + tile) * 4 + quadrant) * 256 + n]
+  int32_t seg_ld = 0, seg_rows = 0;
+  float seg_maxdeg = 0.f;            // longest segment (bound of the sums)
+  float* seg_bound = nullptr;        // device float set to the bound of the segment sums
 };
 
 struct TcChain {

@@ -195,11 +195,13 @@ cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* p
 }
 
 // dst[r, 0:ld_dst] = [src[r, 0:width], 0 ...]: widens rows whose width / stride are not multiples of 64 floats (the 102
-// input features) so that the tensor-core chain can read them with aligned 128-bit loads.
+// input features) so that the tensor-core chain can read them with aligned 128-bit loads.  The pass sees every input value,
+// so it also produces their absolute maximum (amax, may be null): the magnitude bound the chain's operand scaling starts from.
 __global__ void __launch_bounds__(256) gw_pad_rows_kernel(const float* __restrict__ src, int ld_src, int width, float* __restrict__ dst,
-                                                          int ld_dst, long long rows) {
+                                                          int ld_dst, long long rows, float* __restrict__ amax) {
   const int q = ld_dst >> 2;  // float4 per destination row
   const long long total = rows * q;
+  float m = 0.f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / q;
     const int c = (int)(e - r * q) * 4;
@@ -209,13 +211,87 @@ __global__ void __launch_bounds__(256) gw_pad_rows_kernel(const float* __restric
     v.y = (c + 1 < width) ? __ldg(s + 1) : 0.f;
     v.z = (c + 2 < width) ? __ldg(s + 2) : 0.f;
     v.w = (c + 3 < width) ? __ldg(s + 3) : 0.f;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     *reinterpret_cast<float4*>(dst + r * ld_dst + c) = v;
   }
+  if (amax) {
+    if (!(m <= 3.0e38f)) m = __int_as_float(0x7f800000);  // NaN / inf inputs: the bound is infinite (the chain flags it)
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));  // m >= 0: int order == float order
+  }
 }
-cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, cudaStream_t stream) {
+cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, float* amax, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   if (ld_dst & 3) return cudaErrorInvalidValue;
-  gw_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>(src, ld_src, width, dst, ld_dst, rows);
+  gw_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>(src, ld_src, width, dst, ld_dst, rows, amax);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// *amax = max(*amax, max |p[0..n)|) over a contiguous array (raw caller tensors entering a tensor-core chain).
+__global__ void __launch_bounds__(256) gw_absmax_flat_kernel(const float* __restrict__ p, long long n, float* __restrict__ amax) {
+  float m = 0.f;
+  const long long head = min(n, (long long)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) >> 2);
+  const long long nv = (n - head) >> 2;
+  const float4* pv = reinterpret_cast<const float4*>(p + head);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nv; e += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(pv + e);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 8) {  // unaligned head and tail
+    for (long long e = threadIdx.x; e < head; e += 8) m = fmaxf(m, fabsf(p[e]));
+    for (long long e = head + 4 * nv + threadIdx.x; e < n; e += 8) m = fmaxf(m, fabsf(p[e]));
+  }
+  if (!(m <= 3.0e38f)) m = __int_as_float(0x7f800000);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+cudaError_t launch_absmax_flat(const float* p, long long n, float* amax, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  gw_absmax_flat_kernel<<<148 * 4, 256, 0, stream>>>(p, n, amax);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- helpers of the fused per-target sums (gw_tc3.cu, F_SEG) ------------------------------------------------------------------
+// stats[0] = longest CSR segment, stats[1] = shortest (caller initialises {0, INT_MAX}); dst[j] = i for ptr[i] <= j < ptr[i+1]
+__global__ void gw_csr_expand_kernel(const int32_t* __restrict__ ptr, int n, int32_t* __restrict__ dst, int* __restrict__ stats) {
+  int mx = 0, mn = 0x7fffffff;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j0 = ptr[i], j1 = ptr[i + 1];
+    mx = max(mx, j1 - j0), mn = min(mn, j1 - j0);
+    if (dst)
+      for (int j = j0; j < j1; ++j) dst[j] = i;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)), mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(stats, mx), atomicMin(stats + 1, mn);
+}
+cudaError_t launch_csr_expand(const int32_t* ptr, int n, int32_t* dst, int* stats, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  gw_csr_expand_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, stream>>>(ptr, n, dst, stats);
+  count_launch();
+  return cudaGetLastError();
+}
+// A segment cut by a 32-row quadrant boundary of the chain kernel's tiles left the sum of its later rows in `carry`
+// ([batch][tiles][4][256]); add it to the segment's row of out.  One 64-thread CTA per (boundary, sample); fixed order.
+__global__ void __launch_bounds__(64) gw_seg_carry_kernel(const float* __restrict__ carry, const int32_t* __restrict__ seg_dst, int rows,
+                                                          int tiles, int seg_rows, float* __restrict__ out, int ldo) {
+  const int bq = blockIdx.x, b = blockIdx.y;  // boundary = tile * 4 + quadrant
+  const int r = (bq >> 2) * 128 + (bq & 3) * 32;
+  if (r <= 0 || r >= rows) return;
+  const int d = __ldg(seg_dst + r);
+  if (__ldg(seg_dst + r - 1) != d) return;  // the quadrant starts a new segment: nothing was carried
+  const float4 c = __ldg(reinterpret_cast<const float4*>(carry + ((size_t)b * tiles * 4 + bq) * 256 + threadIdx.x * 4));
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)b * seg_rows + d) * (size_t)ldo + threadIdx.x * 4);
+  float4 v = *o;
+  v.x += c.x, v.y += c.y, v.z += c.z, v.w += c.w;
+  *o = v;
+}
+cudaError_t launch_seg_carry(const float* carry, const int32_t* seg_dst, int rows, int seg_rows, int batch, float* out, int ldo,
+                             cudaStream_t stream) {
+  if (rows <= 0 || batch <= 0) return cudaSuccess;
+  const int tiles = (rows + 127) / 128;
+  gw_seg_carry_kernel<<<dim3(tiles * 4, batch), 64, 0, stream>>>(carry, seg_dst, rows, tiles, seg_rows, out, ldo);
   count_launch();
   return cudaGetLastError();
 }

@@ -33,6 +33,18 @@
 //     alignment).  setmaxnreg gives the workers 120 registers and the auxiliary warpgroup 32; the lean path has no spills.
 //   * warp 16: weight producer (cp.async.bulk of pre-swizzled 32 KB panels), warp 17: MMA issuer (one thread).
 // TMEM: 512 columns = two 128x256 fp32 accumulators alternating by layer.
+//
+// Round 2:
+//   * tile rows are handed to threads so that a thread's four rows are CONSECUTIVE logical rows (re[k] = 32 q + 4 (lane/4) + k;
+//     the TMEM lane / operand row stays rt[k]); the last layer of an edge chain can then reduce its rows per target node in
+//     registers + two shuffles (graph_net_block.py:188 scatter_sum, edges are target-sorted, segments of <= 8 rows) and store
+//     per-node sums: the decoder's e' rows are never written, the separate segment-sum launches disappear.
+//   * the lean path is shaped at compile time (chunks per source / per layer are template constants): every chunk loop is
+//     fully unrolled, rows are 64-bit pointers resolved once per layer and chunk offsets are immediates; the rolled loops
+//     of round 1 spent ~45 % of their instructions on register rotation and address arithmetic (profiles/r02_*).
+//   * operand range: every tensor carries a rigorous magnitude bound (device float); each CTA derives, per layer, the power
+//     of two that brings the next fp16-split operand under 2^15 and folds its inverse into the accumulator scale, so raw
+//     (unnormalised) inputs cannot overflow fp16.  The amax status bit stays as a guard.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -56,7 +68,7 @@ namespace t3 {
 enum { ABL_FENCE = 1, ABL_LOADS = 2, ABL_CONVERT = 4, ABL_STORES = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
 
 // epilogue feature mask of a layer (TcLayer::kind); the lean path is instantiated for the masks that occur
-enum { F_ADD0 = 1, F_ADD1 = 2, F_RELU = 4, F_LN = 8, F_RES = 16, F_OUT = 32, F_FEEDS = 64 };
+enum { F_ADD0 = 1, F_ADD1 = 2, F_RELU = 4, F_LN = 8, F_RES = 16, F_OUT = 32, F_FEEDS = 64, F_SEG = 128 };
 #ifndef GW_CHUNK_UNROLL
 #define GW_CHUNK_UNROLL 1  // the per-chunk loops stay rolled: unrolled, their code no longer fits the instruction cache
 #endif
@@ -70,7 +82,7 @@ constexpr int WSPLIT = 4;                       // worker warps per TMEM lane qu
 constexpr int WORKER_WARPS = 4 * WSPLIT, NUM_WORKERS = 32 * WORKER_WARPS;
 constexpr int WARP_PRODUCER = WORKER_WARPS, WARP_MMA = WORKER_WARPS + 1;
 constexpr int NUM_THREADS = NUM_WORKERS + 128;  // + one auxiliary warpgroup: producer, MMA issuer, two idle warps
-constexpr int WORKER_REGS = 104, AUX_REGS = 56;  // setmaxnreg: 4 x 32 x 120 + 32 x 32 = 16384 registers per SM sub-partition
+constexpr int WORKER_REGS = 112, AUX_REGS = 48;  // setmaxnreg: 512 x 112 + 128 x 48 = 63488 of 65536 registers
 constexpr int PAR_LAYERS = 6;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;
@@ -80,8 +92,9 @@ constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_PAR = OFF_TMEM + 16;                // float bias[PAR_LAYERS][256]
 constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;  // float gamma_beta[2][2][256]
 constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_x[WSPLIT][128], ln_y[WSPLIT][128]: row statistics exchange
-constexpr int OFF_PRE = OFF_LN + 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather offsets of the coming tile
-constexpr int SMEM_BYTES = OFF_PRE + 8 * NUM_WORKERS * 4;
+constexpr int OFF_PRE = OFF_LN + 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather rows of the coming tile
+constexpr int OFF_SCL = OFF_PRE + 8 * NUM_WORKERS * 4;  // float scl[2 * PAR_LAYERS + 4]: per layer {accumulator scale, operand scale of the result}, then the stage-0 operand scale
+constexpr int SMEM_BYTES = OFF_SCL + (2 * PAR_LAYERS + 4) * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
 
@@ -202,36 +215,52 @@ __device__ __forceinline__ void store_operand16(uint8_t* slot, const int (&rt)[4
 
 // ---- lean full-width path --------------------------------------------------------------------------------------------
 // When every source / output of a layer is 16-byte aligned and at least as wide as the layer (the processor and decoder edge
-// and node passes: >95 % of the run time), a source is a warp-uniform 64-bit base plus four 32-bit byte offsets (one per row
-// of mine), resolved once per layer; every access is base + offset + immediate.  Contiguous sources are addressed relative
-// to the tile's first row, gathered ones relative to the sample (the launcher checks that this fits 32 bits).
-__device__ __forceinline__ const float* row_base(const RowSrc& s, int b, int i0) {
-  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
-  return src_gathered(s.kind) ? base : base + (size_t)i0 * (size_t)s.ld;
+// and node passes: >95 % of the run time), a source is four 64-bit row pointers per thread (one per row of mine, my first
+// column folded in), resolved once per layer; every access is pointer + immediate.
+template <int I, int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
 }
-__device__ __forceinline__ const float* row_refs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, uint32_t (&off)[4]) {
-  const float* base = s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0;
+template <int V>
+using ic = std::integral_constant<int, V>;
+
+__device__ __forceinline__ const char* src_sample_base(const RowSrc& s, int b) {
+  return reinterpret_cast<const char*>(s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0);
+}
+// my four row pointers into a source: tile rows i0 + rl[k] (through the index for gathered sources), first column cofs
+__device__ __forceinline__ void row_ptrs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, const char* (&p)[4]) {
+  const char* base = src_sample_base(s, b) + 4 * cofs;
+  const size_t ldb = 4 * (size_t)s.ld;
   if (src_gathered(s.kind)) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) off[k] = ((uint32_t)__ldg(s.idx + i0 + rl[k]) * (uint32_t)s.ld + (uint32_t)cofs) * 4u;
-    return base;
-  }
+    for (int k = 0; k < 4; ++k) p[k] = base + (size_t)(uint32_t)__ldg(s.idx + i0 + rl[k]) * ldb;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) off[k] = ((uint32_t)rl[k] * (uint32_t)s.ld + (uint32_t)cofs) * 4u;
-  return base + (size_t)i0 * (size_t)s.ld;
+    for (int k = 0; k < 4; ++k) p[k] = base + (size_t)(uint32_t)(i0 + rl[k]) * ldb;
+  }
 }
-// my 16 values at float offset `coff` from the row references: 4 LDG.128
-__device__ __forceinline__ void ldfrag(const float* base, const uint32_t (&off)[4], int coff, float (&o)[16]) {
-  const char* b = reinterpret_cast<const char*>(base + coff);
+// my 16 values at byte offset `off` (a compile-time constant at every call site) from the row pointers: 4 LDG.128.
+// Fragment index of (row k, column c of my four): 8 (k >> 1) + 4 (c >> 1) + 2 (k & 1) + (c & 1).
+__device__ __forceinline__ void ldfrag4(const char* const (&p)[4], int off, float (&o)[16]) {
   float4 t[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(b + off[k]));
+  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(p[k] + off));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = 8 * (k >> 1) + 2 * (k & 1);
     o[i] = t[k].x, o[i + 1] = t[k].y, o[i + 4] = t[k].z, o[i + 5] = t[k].w;
   }
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// v[i] = v[i] * s + b(column of i)   (bias / LayerNorm parameter vectors are float4 per thread)
+__device__ __forceinline__ float col4(const float4& b, int i) { return ((i >> 2) & 1) ? ((i & 1) ? b.w : b.z) : ((i & 1) ? b.y : b.x); }
 // Operand store with precomputed addressing.  `sa` = shared address of (my row 32q + lane/4, my half2, chunk j = 0) inside the
 // slot; the j = 1 chunk is sa ^ 16 (SWIZZLE_128B flips bit 4), my other rows are +8 / +16 / +24 rows = immediates.
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
@@ -258,6 +287,16 @@ __device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)
       }
     }
 }
+
+// ---- operand range --------------------------------------------------------------------------------------------------
+// Power of two s such that a tensor bounded by m has |s x| < 2^15 (fp16 max is 65504); 1 when m is already in range.
+__device__ __forceinline__ float range_scale(float m) {
+  if (!(m > 32768.f)) return 1.f;
+  const int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;  // floor(log2 m): m < 2^(e+1)
+  return __uint_as_float((uint32_t)(127 + 14 - e) << 23);         // 2^(14-e)   (e <= 127 -> exponent field >= 14: normal)
+}
+__device__ __forceinline__ float ldbound(const float* p) { return p ? __ldg(p) : 0.f; }
+__device__ __forceinline__ float srcbound(const RowSrc& s) { return s.bound ? __ldg(s.bound) * s.bound_mul : 0.f; }
 
 // MODE 0: every part takes the general path; 1: every part takes the lean full-width path.  (A third mode that chose per
 // part inside one kernel was measured slower than the general path: the live state of both paths spills.)
@@ -309,6 +348,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         ++ln_slot;
       }
     }
+  }
+  if (threadIdx.x == 32) {
+    // Operand range ladder (one thread; every CTA derives the same numbers from the same inputs).  m = bound of the operand
+    // about to be split, s = its power-of-two scale; layer l multiplies its accumulator by wscale_inv / s and scales its own
+    // result by the next s before splitting it.
+    float* scl = reinterpret_cast<float*>(smem + OFF_SCL);
+    float m = fmaxf(srcbound(ch.a0[0]), srcbound(ch.a0[1]));
+    if (ch.a0[0].kind == SRC_GATHER_BCAST_RELU) m += ldbound(ch.a0[0].bound2);
+    float sc = range_scale(m);
+    bool bad = !(m < 3.0e38f);
+    scl[2 * PAR_LAYERS] = sc;
+    for (int l = 0; l < ch.n_layers; ++l) {
+      const TcLayer& L = ch.layer[l];
+      scl[2 * l] = L.wscale_inv / sc;  // (a reuse_a layer multiplies the same operand: m and sc are unchanged)
+      float mo = L.ln_g ? L.ln_bound : fmaf(m, L.gain, L.off) + srcbound(L.add[0]) + srcbound(L.add[1]);
+      mo += srcbound(L.residual);
+      bad = bad || !(mo < 3.0e38f);
+      if (blockIdx.x == 0) {
+        if (L.out_bound) {  // (two layers may fill halves of one tensor: its bound is the larger one)
+          const bool again = l > 0 && ch.layer[l - 1].out_bound == L.out_bound;
+          *L.out_bound = again ? fmaxf(*L.out_bound, mo) : mo;
+        }
+        if (L.seg_bound) *L.seg_bound = mo * L.seg_maxdeg;
+      }
+      float so = 1.f;
+      if (L.feeds_next) {
+        m = mo;
+        sc = so = range_scale(m);
+      }
+      scl[2 * l + 1] = so;
+    }
+    if (bad && ch.status) atomicOr(ch.status, 8);  // a magnitude bound overflowed fp32: inputs are not finite numbers of usable size
   }
   tc_fence_before();
   __syncthreads();
@@ -416,10 +487,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     const int q = warp & 3;    // TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..+31)
     const int hq = warp >> 2;  // which 16 columns of every 64-column chunk
     const int lr = lane >> 2, lc = lane & 3;
-    int rt[4];  // my four tile rows (= TMEM lanes)
+    int rt[4];  // my four TMEM lanes (= rows of the shared-memory operand)
+    int re[4];  // the LOGICAL tile rows they hold: four consecutive rows per thread, 32 consecutive rows per 8 lane groups
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rt[k] = 32 * q + 16 * (k >> 1) + lr + 8 * (k & 1);
+    for (int k = 0; k < 4; ++k) rt[k] = 32 * q + 16 * (k >> 1) + lr + 8 * (k & 1), re[k] = 32 * q + 4 * lr + k;
     const int cofs = 16 * hq + 4 * lc;  // my first (logical) column inside a 64-column chunk; the operand position uses 2 * lc
+    const float* scl = reinterpret_cast<const float*>(smem + OFF_SCL);
+    const float a0scale = scl[2 * PAR_LAYERS];
     float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
     float* ln_y = ln_x + WSPLIT * 128;
     uint32_t fi = 0, li = 0;
@@ -440,7 +514,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const int nvalid = min(TILE_M, rows - i0);
       int rl[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+      for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
       const int nk0 = ch.K0 >> 6, w0 = ch.a0[0].width;
       int ri[4] = {0, 0, 0, 0}, ri2[4] = {0, 0, 0, 0};  // rows of the current source (and of its broadcast partner)
       int cur_src = -1;
@@ -474,6 +548,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         if (c + 1 < nk0) fetch(c + 1, nxt);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
         if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
+        if (a0scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
+        }
         if (!ABL3(ABL_CONVERT)) store_operand16(smem + OFF_A + slot * A_SLOT_BYTES, rt, hq, lc, cur, split, amax);
         publish(slot);
         tr.ev(500 + c);
@@ -486,268 +564,363 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     // operand-store address of (my first row, chunk j = 0) inside a slot; see store_operand_fast
     const uint32_t sa0 = sbase + OFF_A + (32 * q + lr) * 128 + 4 * lc + (((2 * hq) ^ lr) << 4);
 
-    // gather offsets of layer 0's addends for the tile whose stage 0 ran last (resolved there, so that the index loads do
-    // not sit between two tiles)
+    // gather rows of layer 0's addends for the tile whose stage 0 ran last (resolved there, so that the index loads do
+    // not sit between two tiles); kept in shared memory, one word per thread and row: registers are the scarce resource
     uint32_t* pre_s = reinterpret_cast<uint32_t*>(smem + OFF_PRE) + threadIdx.x;  // [8][NUM_WORKERS], one column per thread
     const bool l0_add0 = ch.layer[0].add[0].kind != SRC_NONE, l0_add1 = ch.layer[0].add[1].kind != SRC_NONE;
+    const bool l0_g0 = src_gathered(ch.layer[0].add[0].kind), l0_g1 = src_gathered(ch.layer[0].add[1].kind);
 
-    // ---- stage 0, lean path: every 64-column chunk lies inside one aligned source -----------------------------------------
-    auto stage0_fast = [&](int tile) {
+    // ---- stage 0, lean path: NC0 + NC1 64-column chunks from one or two aligned sources, fully unrolled ------------------------
+    auto stage0_fast = [&](auto NC0c, auto NC1c, int tile) {
+      constexpr int NC0 = decltype(NC0c)::value, NC1 = decltype(NC1c)::value, NC = NC0 + NC1;
       const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
       const int nvalid = min(TILE_M, rows - i0);
       int rl[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
-      const int nk0 = ch.K0 >> 6, nc0 = ch.a0[0].width >> 6;
-      const float* ba = nullptr;
-      const float* bb = nullptr;
-      uint32_t oa[4] = {0u, 0u, 0u, 0u}, ob[4] = {0u, 0u, 0u, 0u};  // (initialised: arrays assigned only on some paths end up in local memory)
-      bool gbr = false;
-      auto setsrc = [&](const RowSrc& src) {
-        ba = row_refs(src, bs, i0, rl, cofs, oa);
-        gbr = src.kind == SRC_GATHER_BCAST_RELU;
-        if (gbr) {
-          bb = src.base2 + (size_t)i0 * (size_t)src.ld2;
+      for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
+      const char* pa[4];
+      const char* pb[4] = {nullptr, nullptr, nullptr, nullptr};
+      const char* pc[4] = {nullptr, nullptr, nullptr, nullptr};
+      row_ptrs(ch.a0[0], bs, i0, rl, cofs, pa);
+      const bool gbr = ch.a0[0].kind == SRC_GATHER_BCAST_RELU;
+      if (gbr) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ob[k] = ((uint32_t)rl[k] * (uint32_t)src.ld2 + (uint32_t)cofs) * 4u;
-        }
-      };
-      auto fetch = [&](int c, float (&o)[16]) {
-        if (c == nc0) setsrc(ch.a0[1]);
-        const int off = 64 * (c < nc0 ? c : c - nc0);
+        for (int k = 0; k < 4; ++k) pc[k] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + rl[k]) * (size_t)ch.a0[0].ld2 + cofs);
+      }
+      if constexpr (NC1 > 0) row_ptrs(ch.a0[1], bs, i0, rl, cofs, pb);
+      auto fetch = [&](auto cc, float (&o)[16]) {
+        constexpr int c = decltype(cc)::value;
         if (ABL3(ABL_LOADS)) return;
-        ldfrag(ba, oa, off, o);
-        if (gbr) {
-          float t[16];
-          ldfrag(bb, ob, off, t);
+        if constexpr (c < NC0) {
+          ldfrag4(pa, 256 * c, o);
+          if (gbr) {
+            float t[16];
+            ldfrag4(pc, 256 * c, t);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
+            for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
+          }
+        } else {
+          ldfrag4(pb, 256 * (c - NC0), o);
         }
       };
-      float cur[16], nxt[16];
-      setsrc(ch.a0[0]);
-      fetch(0, cur);
-      if (l0_add0) {  // kept in shared memory (one word per thread and row): registers are the scarce resource of the epilogues
-        uint32_t t[4];
-        (void)row_refs(ch.layer[0].add[0], bs, i0, rl, cofs, t);
+      float buf[2][16] = {};
+      fetch(ic<0>{}, buf[0]);
+      if (l0_add0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = t[k];
+        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = l0_g0 ? (uint32_t)__ldg(ch.layer[0].add[0].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
       }
       if (l0_add1) {
-        uint32_t t[4];
-        (void)row_refs(ch.layer[0].add[1], bs, i0, rl, cofs, t);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = t[k];
+        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
       }
-      for (int c = 0; c < nk0; ++c) {
-        if (c + 1 < nk0) fetch(c + 1, nxt);
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        if constexpr (c + 1 < NC) fetch(ic<c + 1>{}, buf[(c + 1) & 1]);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
         if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
+        float(&cur)[16] = buf[c & 1];
+        if (a0scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
+        }
         if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
         publish(slot);
         tr.ev(500 + c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-      }
-      fi += nk0;
+      });
+      fi += NC;
     };
 
-    // ---- one layer's epilogue, lean path: N = 64 np (LayerNorm: N = 256), full-width aligned addends / residual / output ------------------------
-    // Register budget: v[16] + pf0[16] + aux[16] + two row-pointer sets.  `aux` is the add[1] prefetch or, on LayerNorm layers
-    // (which have no addends), the per-row scale/shift; `p1` is the add[1] rows or the output rows (never both: launcher).
-    auto layer_fast = [&](auto FLc, int l, uint32_t acc, uint32_t use, bool waited, int bs, int i0, int nvalid, int ln_slot) {
-      constexpr int F = decltype(FLc)::value;  // >= 0: the layer's feature mask is a compile-time constant
+    // ---- one layer's epilogue, lean path: N = 64 NP, full-width aligned addends / residual / output ---------------------------
+    // Register budget: two accumulator fragments (the chunk in work and the next one in flight from TMEM), the prefetched
+    // addend / residual fragments of the next chunk, and 8 registers of row pointers per global source.
+    auto layer_fast = [&](auto FLc, auto NPc, int l, uint32_t acc, uint32_t use, bool waited, int tile, int ln_slot) {
+      constexpr int F = decltype(FLc)::value, NP = decltype(NPc)::value;
+      constexpr bool has_add0 = (F & F_ADD0) != 0, has_add1 = (F & F_ADD1) != 0, has_res = (F & F_RES) != 0, has_out = (F & F_OUT) != 0;
+      constexpr bool relu = (F & F_RELU) != 0, has_ln = (F & F_LN) != 0, feeds = (F & F_FEEDS) != 0, has_seg = (F & F_SEG) != 0;
+      constexpr bool has0 = has_add0 || has_res;
       const TcLayer& L = ch.layer[l];
-      const float wsi = L.wscale_inv;
-      const int np = L.N >> 6;
-      const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
-      const bool has_add0 = F >= 0 ? (F & F_ADD0) != 0 : L.add[0].kind != SRC_NONE;
-      const bool has_add1 = F >= 0 ? (F & F_ADD1) != 0 : L.add[1].kind != SRC_NONE;
-      const bool has_res = F >= 0 ? (F & F_RES) != 0 : L.residual.kind != SRC_NONE;
-      const bool has_out = F >= 0 ? (F & F_OUT) != 0 : L.out != nullptr;
-      const bool relu = F >= 0 ? (F & F_RELU) != 0 : L.relu != 0;
-      const bool has_ln = F >= 0 ? (F & F_LN) != 0 : L.ln_g != nullptr;
-      const bool feeds = F >= 0 ? (F & F_FEEDS) != 0 : L.feeds_next != 0;
-      const uint32_t g_o = OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_o = g_o + 1024;
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      const float wsi = scl[2 * l], osc = scl[2 * l + 1];
+      const uint32_t bias_a = sbase + OFF_PAR + 4 * cofs + l * 1024;
+      const uint32_t g_a = sbase + OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_a = g_a + 1024;
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
       const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
-      const bool has0 = (has_add0 || has_res) && !ABL3(ABL_LOADS), has1 = has_add1 && !ABL3(ABL_LOADS);
-      const float* b0 = nullptr;  // pf0 source
-      const float* b1 = nullptr;  // add[1] source, or the output rows
-      uint32_t o0[4] = {0u, 0u, 0u, 0u}, o1[4] = {0u, 0u, 0u, 0u};  // (initialised: see stage0_fast)
-      float pf0[16] = {}, aux[16] = {};
+      const char* p0[4] = {nullptr, nullptr, nullptr, nullptr};  // addend 0 or residual rows
+      const char* p1[4] = {nullptr, nullptr, nullptr, nullptr};  // addend 1 rows
+      float pf0[16] = {}, pf1[16] = {};
       {
         int rl[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
-        if (l == 0 && has_add0) {  // resolved during this tile's stage 0
-          b0 = row_base(src0, bs, i0);
+        for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
+        if constexpr (has0) {
+          if (l == 0 && has_add0) {  // rows resolved during this tile's stage 0
+            const char* base = src_sample_base(src0, bs) + 4 * cofs;
+            const size_t ldb = 4 * (size_t)src0.ld;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o0[k] = pre_s[k * NUM_WORKERS];
-        } else if (has0) {
-          b0 = row_refs(src0, bs, i0, rl, cofs, o0);
+            for (int k = 0; k < 4; ++k) p0[k] = base + (size_t)pre_s[k * NUM_WORKERS] * ldb;
+          } else {
+            row_ptrs(src0, bs, i0, rl, cofs, p0);
+          }
         }
-        if (l == 0 && has1) {
-          b1 = row_base(L.add[1], bs, i0);
+        if constexpr (has_add1) {
+          if (l == 0) {
+            const char* base = src_sample_base(L.add[1], bs) + 4 * cofs;
+            const size_t ldb = 4 * (size_t)L.add[1].ld;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o1[k] = pre_s[(4 + k) * NUM_WORKERS];
-        } else if (has1) {
-          b1 = row_refs(L.add[1], bs, i0, rl, cofs, o1);
+            for (int k = 0; k < 4; ++k) p1[k] = base + (size_t)pre_s[(4 + k) * NUM_WORKERS] * ldb;
+          } else {
+            row_ptrs(L.add[1], bs, i0, rl, cofs, p1);
+          }
         }
       }
-      if (has0 && !has_ln) ldfrag(b0, o0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
-      if (has1) ldfrag(b1, o1, 0, aux);
+      const bool ld_on = !ABL3(ABL_LOADS);
+      if constexpr (has0 && !has_ln) {
+        if (ld_on) ldfrag4(p0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
+      }
+      if constexpr (has_add1) {
+        if (ld_on) ldfrag4(p1, 0, pf1);
+      }
       if (!waited) {
         tr.ev(600 + l);
         mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
         tc_fence_after();
         tr.ev(610 + l);
       }
-      if (has_ln) {  // LayerNorm as v * aux[k] + aux[4 + k] per row
+      float rs[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};  // LayerNorm as v * rs[k] + sh[k] per row
+      if constexpr (has_ln) {
+        if (!ABL3(ABL_LN)) {
+          float pv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          static_for<0, NP>([&](auto sc_) {
+            constexpr int s = decltype(sc_)::value;
+            float v[16];
+            tmem_ld_16x256b_x2(taddr + 64 * s, v);
+            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+            tmem_wait_ld();
+            const float4 b4 = lds128(bias_a + 256 * s);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) aux[k] = 1.f, aux[4 + k] = 0.f;
-      }
-      if (has_ln && !ABL3(ABL_LN)) {
-        float pv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll CHUNK_UNROLL
-        for (int s = 0; s < 4; ++s) {
-          float v[16];
-          tmem_ld_16x256b_x2(taddr + 64 * s, v);
-          tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
-          tmem_wait_ld();
-          const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col4(b4, i));
+            if constexpr (s == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
-          if (s == 0) {
+              for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
+            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
+            for (int i = 0; i < 16; ++i) {
+              const int k = 2 * (i >> 3) + ((i >> 1) & 1);
+              const float d = v[i] - pv[k];
+              s1[k] += d;
+              s2[k] = fmaf(d, d, s2[k]);
+            }
+          });
+          if constexpr (has0) {
+            if (ld_on) ldfrag4(p0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = 2 * (i >> 3) + ((i >> 1) & 1);
-            const float d = v[i] - pv[k];
-            s1[k] += d;
-            s2[k] = fmaf(d, d, s2[k]);
-          }
-        }
-        if (has0) ldfrag(b0, o0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
-        float mean[4], m2[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = s1[k] * (1.0f / 16.0f);
-          mean[k] = pv[k] + a;
-          m2[k] = fmaxf(s2[k] - s1[k] * a, 0.f);
-        }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
+          float mean[4], m2[4];
+          constexpr float inv_cnt = 1.0f / (4.0f * NP);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float mb = __shfl_xor_sync(0xffffffffu, mean[k], o), qb = __shfl_xor_sync(0xffffffffu, m2[k], o);
-            const float d = mb - mean[k];
-            mean[k] = 0.5f * (mean[k] + mb);
-            m2[k] = (m2[k] + qb) + d * d * (o == 1 ? 8.0f : 16.0f);
+            const float a = s1[k] * inv_cnt;
+            mean[k] = pv[k] + a;
+            m2[k] = fmaxf(s2[k] - s1[k] * a, 0.f);
           }
-        }
-        if (lc == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+          for (int o = 1; o <= 2; o <<= 1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float n = 0.f, mu = 0.f, q2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < WSPLIT; ++w) {  // same order in every thread of the row; 64 values per warp partial
-            const float mw = ln_x[w * 128 + rt[k]], qw = ln_y[w * 128 + rt[k]];
-            const float d = mw - mu, nt = n + 64.f;
-            mu += d * (64.f / nt);
-            q2 += qw + d * d * (n * 64.f / nt);
-            n = nt;
+            for (int k = 0; k < 4; ++k) {
+              const float mb = __shfl_xor_sync(0xffffffffu, mean[k], o), qb = __shfl_xor_sync(0xffffffffu, m2[k], o);
+              const float d = mb - mean[k];
+              mean[k] = 0.5f * (mean[k] + mb);
+              m2[k] = (m2[k] + qb) + d * d * (o == 1 ? 2.0f * NP : 4.0f * NP);
+            }
           }
-          const float rstd = 1.0f / sqrtf(q2 * (1.0f / 256.0f) + 1e-5f);
-          aux[k] = rstd, aux[4 + k] = -mu * rstd;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
-      }
-      if (has_ln && ABL3(ABL_LN) && has0) ldfrag(b0, o0, 0, pf0);
-      if (has_out) {
-        b1 = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo;
+          if (lc == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o1[k] = ((uint32_t)rt[k] * (uint32_t)L.ldo + (uint32_t)cofs) * 4u;
+            for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+          constexpr float nw = 16.0f * NP;  // values per warp partial
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float n = 0.f, mu = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WSPLIT; ++w) {  // same order in every thread of the row
+              const float mw = ln_x[w * 128 + rt[k]], qw = ln_y[w * 128 + rt[k]];
+              const float d = mw - mu, nt = n + nw;
+              mu += d * (nw / nt);
+              q2 += qw + d * d * (n * nw / nt);
+              n = nt;
+            }
+            const float rstd = 1.0f / sqrtf(q2 * (1.0f / (64.0f * NP)) + 1e-5f);
+            rs[k] = rstd, sh[k] = -mu * rstd;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
+        } else if constexpr (has0) {
+          if (ld_on) ldfrag4(p0, 0, pf0);
+        }
       }
-      // The accumulator chunk s+1 is fetched from TMEM (into vn) while chunk s is processed (in v).
-      float vn[16] = {};
+      // output rows (fp32): row pointers + store predicates
+      char* po[4] = {nullptr, nullptr, nullptr, nullptr};
+      if constexpr (has_out) {
+        char* ob = reinterpret_cast<char*>(L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo + cofs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) po[k] = ob + (size_t)(uint32_t)re[k] * (4 * (size_t)L.ldo);
+      }
+      // fused per-target sums: which of my four consecutive rows start a new target, and who owns which piece
+      bool b1 = false, b2 = false, b3 = false, tail_st = false, head_st = false, inner_any = false;
+      float c1f = 0.f, c2f = 0.f;
+      char* tail_p = nullptr;
+      char* head_p = nullptr;
+      int dseg[4] = {0, 0, 0, 0};
+      bool b0 = false;
+      if constexpr (has_seg) {
+        const int32_t* sd = L.seg_dst + i0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dseg[k] = (re[k] < nvalid) ? __ldg(sd + re[k]) : -1 - k;
+        int dprev = __shfl_up_sync(0xffffffffu, dseg[3], 4);
+        if (lr == 0) dprev = (i0 + 32 * q > 0 && 32 * q < nvalid) ? __ldg(sd + 32 * q - 1) : -1 - 7;
+        b0 = dseg[0] != dprev, b1 = dseg[1] != dseg[0], b2 = dseg[2] != dseg[1], b3 = dseg[3] != dseg[2];
+        const bool in123 = b1 || b2 || b3;
+        const uint32_t nb0 = __shfl_down_sync(0xffffffffu, (uint32_t)b0, 4), nin = __shfl_down_sync(0xffffffffu, (uint32_t)in123, 4);
+        const uint32_t nnb0 = __shfl_down_sync(0xffffffffu, (uint32_t)b0, 8);
+        const bool cont1 = lr < 7 && !nb0;                          // my last piece continues into the next thread's rows
+        const bool cont2 = cont1 && !nin && lr < 6 && !nnb0;        // ... and through all of them into the one after
+        c1f = cont1 ? 1.f : 0.f, c2f = cont2 ? 1.f : 0.f;
+        // the piece that ends with my row 3 is mine to store if it starts inside my rows, or if I hold the first rows of the
+        // quadrant (then it continues a segment of the previous quadrant / tile and goes to the carry buffer)
+        const bool starts_here = b0 || in123;
+        char* carry = reinterpret_cast<char*>(L.seg_carry + ((((size_t)bs * tiles_per_sample + (size_t)(i0 / TILE_M)) * 4 + q) * 256 + 64 * 0 + cofs));
+        if (starts_here) {
+          tail_st = dseg[3] >= 0;
+          tail_p = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)max(dseg[3], 0)) * (size_t)L.seg_ld + cofs);
+        } else if (lr == 0) {
+          tail_st = dseg[3] >= 0;
+          tail_p = carry;
+        }
+        // the quadrant's first thread also owns the piece BEFORE its first inner boundary when that piece continues the previous
+        // quadrant (the usual case: 32 is no multiple of the segment length): its sum is H below and goes to the carry buffer
+        head_st = lr == 0 && !b0 && in123 && dseg[0] >= 0;
+        head_p = carry;
+        // pieces that start AND end inside my four rows (segments shorter than four rows; never on the icosahedral graphs)
+        inner_any = __any_sync(0xffffffffu, (b1 && b0) || (b2 && (b0 || b1)) || (b3 && (b0 || b1 || b2)));
+      }
+      // The accumulator chunk s+1 is fetched from TMEM while chunk s is processed.
+      float vb[2][16] = {};
       if (!ABL3(ABL_TMEM)) {
-        tmem_ld_16x256b_x2(taddr, vn);
-        tmem_ld_16x256b_x2(taddr + (16u << 16), vn + 8);
+        tmem_ld_16x256b_x2(taddr, vb[0]);
+        tmem_ld_16x256b_x2(taddr + (16u << 16), vb[0] + 8);
       }
-#pragma unroll CHUNK_UNROLL
-      for (int s = 0; s < np; ++s) {
-        float v[16];
-        tmem_wait_ld_into(vn);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = vn[i];
-        if (s + 1 < np && !ABL3(ABL_TMEM)) {
-          tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vn);
-          tmem_ld_16x256b_x2(taddr + 64 * (s + 1) + (16u << 16), vn + 8);
-        }
-        if (s + 1 == np) {  // my last read of this accumulator
+      static_for<0, NP>([&](auto sc_) {
+        constexpr int s = decltype(sc_)::value;
+        float(&v)[16] = vb[s & 1];
+        tmem_wait_ld_into(v);
+        if constexpr (s + 1 < NP) {
+          if (!ABL3(ABL_TMEM)) {
+            tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vb[(s + 1) & 1]);
+            tmem_ld_16x256b_x2(taddr + 64 * (s + 1) + (16u << 16), vb[(s + 1) & 1] + 8);
+          }
+        } else {  // my last read of this accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
         }
-        const float4 b4 = *reinterpret_cast<const float4*>(smem + bias_o + 256 * s);
+        const float4 b4 = lds128(bias_a + 256 * s);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, ((i >> 2) & 1) ? ((i & 1) ? b4.w : b4.z) : ((i & 1) ? b4.y : b4.x));
-        if (has_add0 && has0) {
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col4(b4, i));
+        if constexpr (has_add0) {
+          if (ld_on) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+          }
         }
-        if (has1) {
+        if constexpr (has_add1) {
+          if (ld_on) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += aux[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf1[i];
+          }
         }
-        if (relu) {
+        if constexpr (relu) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (has_ln) {
-          const float4 g4 = *reinterpret_cast<const float4*>(smem + g_o + 256 * s);
-          const float4 e4 = *reinterpret_cast<const float4*>(smem + b_o + 256 * s);
+        if constexpr (has_ln) {
+          const float4 g4 = lds128(g_a + 256 * s), e4 = lds128(b_a + 256 * s);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int k = 2 * (i >> 3) + ((i >> 1) & 1);
-            const float gx = ((i >> 2) & 1) ? ((i & 1) ? g4.w : g4.z) : ((i & 1) ? g4.y : g4.x);
-            const float ex = ((i >> 2) & 1) ? ((i & 1) ? e4.w : e4.z) : ((i & 1) ? e4.y : e4.x);
-            v[i] = fmaf(fmaf(v[i], aux[k], aux[4 + k]), gx, ex);
+            v[i] = fmaf(fmaf(v[i], rs[k], sh[k]), col4(g4, i), col4(e4, i));
           }
         }
-        if (!has_add0 && has0) {
+        if constexpr (has_res) {
+          if (ld_on) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+          }
         }
-        if (s + 1 < np) {  // next chunk's global operands: in flight while this chunk is stored / converted
-          if (has0) ldfrag(b0, o0, 64 * (s + 1), pf0);
-          if (has1) ldfrag(b1, o1, 64 * (s + 1), aux);
+        if constexpr (s + 1 < NP) {  // next chunk's global operands: in flight while this chunk is stored / converted
+          if constexpr (has0) {
+            if (ld_on) ldfrag4(p0, 256 * (s + 1), pf0);
+          }
+          if constexpr (has_add1) {
+            if (ld_on) ldfrag4(p1, 256 * (s + 1), pf1);
+          }
         }
-        if (has_out && !ABL3(ABL_STORES)) {
+        if constexpr (has_out) {
+          if (!ABL3(ABL_STORES)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (rt[k] < nvalid) {
-              const int i = 8 * (k >> 1) + 2 * (k & 1);
-              char* o = reinterpret_cast<char*>(const_cast<float*>(b1) + 64 * s) + o1[k];
-              *reinterpret_cast<float4*>(o) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+            for (int k = 0; k < 4; ++k) {
+              if (re[k] < nvalid) {
+                const int i = 8 * (k >> 1) + 2 * (k & 1);
+                *reinterpret_cast<float4*>(po[k] + 256 * s) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+              }
             }
           }
         }
-        if (feeds) {
+        if constexpr (has_seg) {
+          // running sums over my four consecutive rows, restarted at every boundary; T = the piece ending with my row 3,
+          // H = the piece before my first inner boundary (all four rows if there is none): what earlier threads add to theirs
+          float T[4], H[4], r0[4], r1[4], r2[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int ci = 4 * (c >> 1) + (c & 1);
+            const float x0 = v[ci], x1 = v[ci + 2], x2 = v[ci + 8], x3 = v[ci + 10];
+            r0[c] = x0;
+            r1[c] = b1 ? x1 : r0[c] + x1;
+            r2[c] = b2 ? x2 : r1[c] + x2;
+            T[c] = b3 ? x3 : r2[c] + x3;
+            H[c] = b1 ? r0[c] : (b2 ? r1[c] : (b3 ? r2[c] : T[c]));
+          }
+          if (head_st && !ABL3(ABL_STORES)) *reinterpret_cast<float4*>(head_p + 256 * s) = make_float4(H[0], H[1], H[2], H[3]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float h1 = __shfl_down_sync(0xffffffffu, H[c], 4), h2 = __shfl_down_sync(0xffffffffu, H[c], 8);
+            T[c] = fmaf(c2f, h2, fmaf(c1f, h1, T[c]));
+          }
+          if (tail_st && !ABL3(ABL_STORES)) *reinterpret_cast<float4*>(tail_p + 256 * s) = make_float4(T[0], T[1], T[2], T[3]);
+          if (inner_any) {
+#pragma unroll
+            for (int j = 1; j <= 3; ++j) {
+              const bool bj = j == 1 ? b1 : (j == 2 ? b2 : b3);
+              const bool started = j == 1 ? b0 : (j == 2 ? (b0 || b1) : (b0 || b1 || b2));
+              if (bj && started && dseg[j - 1] >= 0) {
+                const float(&rr)[4] = j == 1 ? r0 : (j == 2 ? r1 : r2);
+                char* dp = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)dseg[j - 1]) * (size_t)L.seg_ld + cofs);
+                *reinterpret_cast<float4*>(dp + 256 * s) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+              }
+            }
+          }
+        }
+        if constexpr (feeds) {
           const uint32_t slot = (fi + s) % A_SLOTS;
+          if (osc != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= osc;
+          }
           if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
           publish(slot);
         }
         tr.ev(700 + 10 * l + s);
-      }
-      if (feeds) fi += np;
+      });
+      if constexpr (feeds) fi += NP;
     };
 
     const int n_layers = ch.n_layers;
@@ -758,7 +931,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const int next_tile = tile + gridDim.x;
       int rl[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) rl[k] = min(rt[k], nvalid - 1);
+      for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
       int ln_slot = 0;
       // l == -1 (first tile only): this tile's own stage 0.  Afterwards stage 0 of tile t+1 runs inside tile t's last layer.
       for (int l = first_tile ? -1 : 0; l < n_layers; ++l) {
@@ -772,7 +945,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           const int t = l < 0 ? tile : next_tile;
           if (t < num_tiles) {
             if constexpr (MODE == 1) {
-              stage0_fast(t);
+              if (ch.a0[1].kind != SRC_NONE) stage0_fast(ic<4>{}, ic<4>{}, t);          // node chains: [x | aggregate]
+              else if (ch.K0 == 256) stage0_fast(ic<4>{}, ic<0>{}, t);                  // edge chains, products of x
+              else stage0_fast(ic<2>{}, ic<0>{}, t);                                    // widened feature rows (K0 = 128)
             } else {
               stage0(t);
             }
@@ -786,18 +961,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
         if constexpr (MODE == 1) {
-#define GW_LF(M) case (M): layer_fast(std::integral_constant<int, (M)>{}, l, acc, use, last_layer, bs, i0, nvalid, ln_slot); break
+#define GW_LF(M, NP_) layer_fast(ic<(M)>{}, ic<(NP_)>{}, l, acc, use, last_layer, tile, ln_slot)
+#define GW_LF4(M) case (M): GW_LF(M, 4); break
+#define GW_LF24(M) case (M): if (L.N == 256) GW_LF(M, 4); else GW_LF(M, 2); break
           switch (L.kind) {
-            GW_LF(F_ADD0 | F_ADD1 | F_RELU | F_FEEDS);  // edge layer 1: gathered P[src] + P[dst]
-            GW_LF(F_ADD0 | F_RELU | F_FEEDS);           // encoder edge layer 1: broadcast constant term
-            GW_LF(F_RELU | F_FEEDS);                    // hidden layers
-            GW_LF(F_LN | F_RES | F_OUT);                // last layer of an edge / node MLP
-            GW_LF(F_LN | F_RES | F_OUT | F_FEEDS);      // ... whose rows are also the operand of the next block's P products
-            GW_LF(F_LN | F_FEEDS);                      // LayerNorm feeding the next MLP of the same chain
-            GW_LF(F_OUT);                               // per-node products P = x W^T
-            GW_LF(F_RELU | F_OUT);
-            default: layer_fast(std::integral_constant<int, -1>{}, l, acc, use, last_layer, bs, i0, nvalid, ln_slot); break;
+            GW_LF4(F_ADD0 | F_ADD1 | F_RELU | F_FEEDS);  // edge layer 1: gathered P[src] + P[dst]
+            GW_LF4(F_ADD0 | F_RELU | F_FEEDS);           // encoder edge layer 1: broadcast constant term
+            GW_LF24(F_RELU | F_FEEDS);                   // hidden layers (N = 128: node_decoder)
+            GW_LF4(F_LN | F_RES | F_OUT);                // last layer of an edge / node MLP
+            GW_LF4(F_LN | F_RES | F_OUT | F_SEG);        // ... of the processor's edge MLP: e' rows and their per-node sums
+            GW_LF4(F_LN | F_RES | F_SEG);                // ... of the decoder's edge MLP: per-point sums only, e' is never written
+            GW_LF4(F_LN | F_RES | F_OUT | F_FEEDS);      // ... whose rows are also the operand of the next block's P products
+            GW_LF4(F_LN | F_FEEDS);                      // LayerNorm feeding the next MLP of the same chain
+            GW_LF4(F_OUT);                               // per-node products P = x W^T
+            GW_LF24(F_RELU | F_OUT);
+            default: break;                              // (the launcher sends chains with any other layer to the general path)
           }
+#undef GW_LF24
+#undef GW_LF4
 #undef GW_LF
           if (has_ln) ++ln_slot;
           ++li;
@@ -806,7 +987,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         const int N = L.N, nval = L.n_valid;
         const int np = (N + 63) >> 6;
-        const float wsi = L.wscale_inv;
+        const float wsi = scl[2 * l], osc = scl[2 * l + 1];
         const uint32_t bias_o = OFF_PAR + 4 * cofs + l * 1024;
         const bool has_add0 = L.add[0].kind != SRC_NONE, has_add1 = L.add[1].kind != SRC_NONE;
         const bool has_res = L.residual.kind != SRC_NONE, has_out = L.out != nullptr;
@@ -974,16 +1155,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               if (inside && vec4_ok(ob - col, L.ldo)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if (rt[k] < nvalid) {
+                  if (re[k] < nvalid) {
                     const int i = 8 * (k >> 1) + 2 * (k & 1);
-                    *reinterpret_cast<float4*>(ob + (size_t)rt[k] * (size_t)L.ldo) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+                    *reinterpret_cast<float4*>(ob + (size_t)re[k] * (size_t)L.ldo) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
                   }
                 }
               } else if (inside && vec2_ok(ob - col, L.ldo)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if (rt[k] < nvalid) {
-                    float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
+                  if (re[k] < nvalid) {
+                    float* orow = ob + (size_t)re[k] * (size_t)L.ldo;
                     const int i = 8 * (k >> 1) + 2 * (k & 1);
                     *reinterpret_cast<float2*>(orow) = make_float2(v[i], v[i + 1]);
                     *reinterpret_cast<float2*>(orow + 2) = make_float2(v[i + 4], v[i + 5]);
@@ -992,8 +1173,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if (rt[k] < nvalid) {
-                    float* orow = ob + (size_t)rt[k] * (size_t)L.ldo;
+                  if (re[k] < nvalid) {
+                    float* orow = ob + (size_t)re[k] * (size_t)L.ldo;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 2 * j;
@@ -1007,6 +1188,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           }
           if (feeds) {
             const uint32_t slot = (fi + s) % A_SLOTS;
+            if (osc != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= osc;
+            }
             if (!ABL3(ABL_CONVERT)) store_operand16(smem + OFF_A + slot * A_SLOT_BYTES, rt, hq, lc, v, split, amax);
             publish(slot);
           }
@@ -1047,36 +1232,46 @@ static bool src_fast(const RowSrc& s, int need) {
 // Marks which parts of a chain take the lean full-width path (ch.fast) and the epilogue kind of every layer.
 static void tc3_mark_lean(TcChain& ch) {
   using namespace t3;
-  // which parts take the lean full-width path
   ch.fast = 0;
-  {
+  {  // stage 0: one 128- or 256-wide aligned source, or two 256-wide ones (the shapes stage0_fast is instantiated for)
     bool ok = true;
     int wsum = 0;
     for (int a = 0; a < 2; ++a) {
       const RowSrc& s = ch.a0[a];
       if (s.kind == SRC_NONE) continue;
       const bool gbr = s.kind == SRC_GATHER_BCAST_RELU;
-      ok = ok && (simple_kind(s.kind) || gbr) && !(s.width & 63) && aligned16(s.base + s.col0) && !(s.ld & 3) && fits32(s);
+      ok = ok && (simple_kind(s.kind) || gbr) && aligned16(s.base + s.col0) && !(s.ld & 3);
       if (gbr) ok = ok && aligned16(s.base2) && !(s.ld2 & 3);
       wsum += s.width;
     }
-    if (ok && wsum == ch.K0 && ch.a0[0].kind != SRC_NONE) ch.fast |= (int32_t)0x80000000u;
+    const bool two = ch.a0[1].kind != SRC_NONE;
+    ok = ok && ch.a0[0].kind != SRC_NONE && wsum == ch.K0;
+    ok = ok && (two ? (ch.a0[0].width == 256 && ch.a0[1].width == 256) : (ch.K0 == 256 || ch.K0 == 128));
+    if (ok) ch.fast |= (int32_t)0x80000000u;
   }
+  static const int kinds4[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,
+                               F_LN | F_RES | F_OUT | F_SEG, F_LN | F_RES | F_SEG, F_LN | F_RES | F_OUT | F_FEEDS, F_LN | F_FEEDS, F_OUT,
+                               F_RELU | F_OUT};
+  static const int kinds2[] = {F_RELU | F_FEEDS, F_RELU | F_OUT};
   for (int l = 0; l < ch.n_layers; ++l) {
     const TcLayer& L = ch.layer[l];
-    bool ok = (L.N == 256 || (L.N == 128 && !L.ln_g)) && L.n_valid == L.N;
+    bool ok = (L.N == 256 || L.N == 128) && L.n_valid == L.N;
     for (int a = 0; a < 2; ++a)
       if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], L.N);
     if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, L.N);
-    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= L.N && L.add[1].kind == SRC_NONE && L.ldo < (1 << 20);
-    if (ok) ch.fast |= 1 << l;
+    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= L.N;
+    if (L.seg_dst) ok = ok && L.seg_out && L.seg_carry && aligned16(L.seg_out) && !(L.seg_ld & 3) && L.ln_g && L.N == 256;
     const int f = (L.add[0].kind != SRC_NONE ? F_ADD0 : 0) | (L.add[1].kind != SRC_NONE ? F_ADD1 : 0) | (L.relu ? F_RELU : 0) |
-                  (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0);
-    static const int kinds[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,
-                                F_LN | F_FEEDS, F_OUT, F_RELU | F_OUT, F_LN | F_RES | F_OUT | F_FEEDS};
-    ch.layer[l].kind = -1;
-    for (int k : kinds)
-      if (k == f) ch.layer[l].kind = f;
+                  (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0) |
+                  (L.seg_dst ? F_SEG : 0);
+    bool listed = false;
+    if (L.N == 256) {
+      for (int k : kinds4) listed = listed || k == f;
+    } else {
+      for (int k : kinds2) listed = listed || k == f;
+    }
+    ch.layer[l].kind = listed ? f : -1;
+    if (ok && listed) ch.fast |= 1 << l;
   }
 }
 cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
@@ -1133,6 +1328,9 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
   // (mode 2, per-part selection inside one kernel, measured slower than the general path: both paths' live state spills)
   const int mode = ch.fast == all ? 1 : 0;
+  if (mode == 0)
+    for (int l = 0; l < ch.n_layers; ++l)
+      if (ch.layer[l].seg_dst) return cudaErrorInvalidValue;  // the fused per-target sum exists on the lean path only
   for (int a = 0; a < 2; ++a)
     if (ch.a0[a].kind == SRC_SEGSUM) return cudaErrorInvalidValue;  // reduce with gw_segsum_kernel first (a fused per-thread
                                                                     // reduction in stage 0 was measured slower than the kernel)

@@ -121,7 +121,9 @@ int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
 
 /* Synchronises `stream` and returns (then clears) the plan's device status word: 0 = ok;
  * bit 0: an activation left the fp16 range in GW_PREC_FP32_TC (results invalid: rerun with GW_PREC_FP32_SIMT);
- * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment.  Non-zero must be treated as failure. */
+ * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment; bit 3: a magnitude bound overflowed (inf / nan
+ * inputs).  Non-zero must be treated as failure.  (Operands are range-scaled from rigorous per-tensor magnitude bounds, so
+ * bit 0 is a guard that finite inputs cannot trip.) */
 int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
 /* Non-blocking read of the same word (it lives in host-mapped memory): reflects every kernel that has COMPLETED so far
  * and does not clear it.  The Python wrappers peek before and after every forward and escalate to gw_plan_status

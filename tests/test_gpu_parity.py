@@ -381,3 +381,29 @@ def test_assimilator_rebuilds_the_observation_graph(precision):
         del obs_gpu
         ref = restate.assimilator_forward(sd, g_static, x, obs)
         assert float((out - ref).abs().max()) < TOL, trial
+
+
+@pytest.mark.parametrize("scale", [1.0e5, 3.0e-4])
+def test_raw_magnitude_inputs_are_range_scaled(scale):
+    """Unnormalised inputs (geopotential ~ 1e5, pressure in Pa; the reference takes them as they are): the fp16-split operands
+    of the tcgen05 path are range-scaled from per-tensor magnitude bounds, so the result matches the oracle at 1e-4 RELATIVE to
+    the output magnitude and no status bit is raised."""
+    from graph_weather_b200 import GraphWeatherForecaster
+    from oracle import restate, weights
+
+    ll = _grid(10)
+    sd = weights.make_state_dict(weights.forecaster_shapes(), 15)
+    x = weights.make_features(2, len(ll), 102, 15)
+    x[..., 5:40] *= scale  # a block of raw-magnitude channels beside O(1) ones (some of them among the 78 residual features)
+    model = GraphWeatherForecaster(ll).cuda().eval()
+    model.load_state_dict(sd)
+    out = model(x.cuda()).cpu()
+    model._engine.plan.status()  # no overflow / bound fault
+    ref = restate.forecaster_forward(sd, restate.build_forecaster_graphs(ll), x)
+    # the 78 residual channels carry the raw inputs themselves (out = increment + input, decoder.py:93): element-wise bound of
+    # 1e-4 on the O(1) increment plus two fp32 ulps of the raw-magnitude term both sides add
+    excess = (out - ref).abs() - (1e-4 + 3e-7 * ref.abs())
+    print(f"raw-magnitude x{scale:g}: max|gpu - oracle| = {float((out - ref).abs().max()):.3e}, max |ref| = {float(ref.abs().max()):.3e}, "
+          f"on O(1) channels {float((out - ref)[..., 40:].abs().max()):.3e}")
+    assert float(excess.max()) <= 0.0
+    assert float((out - ref)[..., 40:].abs().max()) < 1e-4  # channels whose inputs are O(1): plain 1e-4
