@@ -3,6 +3,7 @@
 Public names mirror graph_weather/__init__.py:3-9 and graph_weather/models/__init__.py:3-17 for the hot path only.
 """
 
+from .constraint import PhysicalConstraintLayer  # noqa: F401
 from .losses import NormalizedMSELoss  # noqa: F401
 from .models import (  # noqa: F401
     AssimilatorDecoder,
@@ -21,5 +22,5 @@ from .models import (  # noqa: F401
 __all__ = [
     "GraphWeatherForecaster", "GraphWeatherForecasterConfig", "GraphWeatherAssimilator", "GraphWeatherAssimilatorConfig",
     "GraphCast", "GraphCastConfig", "Encoder", "Processor", "Decoder", "AssimilatorEncoder", "AssimilatorDecoder",
-    "NormalizedMSELoss",
+    "NormalizedMSELoss", "PhysicalConstraintLayer",
 ]  # fmt: skip

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "gw_timing_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double), _vp]),
     "gw_loss_workspace_bytes": (_i64, []),
     "gw_normalized_mse_loss_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "gw_forward_strided": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "gw_constraint_workspace_bytes": (_i64, [_i64, _i32]),
+    "gw_constraint_apply": (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, ctypes.c_float, _vp, _vp]),
     "gw_launch_count": (_i64, []),
     "gw_launch_count_reset": (None, []),
 }
@@ -198,11 +201,18 @@ class Plan:
             _check(self.lib.gw_plan_set_weights(self.handle, arr, len(items), _stream(d)))
             torch.cuda.current_stream(d).synchronize()
 
-    def forward(self, features, out):
+    def forward(self, features, out, out_ld=None):
+        """out: [batch, n_out, out_dim] contiguous, or (out_ld given) the first out_dim columns of rows `out_ld` floats apart."""
         d = self.device
         with torch.cuda.device(d):
-            _check(self.lib.gw_forward(self.handle, _ptr(features, torch.float32, d), _ptr(out, torch.float32, d),
-                                       int(features.shape[0]), _stream(d)))  # fmt: skip
+            if out_ld is None:
+                _check(self.lib.gw_forward(self.handle, _ptr(features, torch.float32, d), _ptr(out, torch.float32, d),
+                                           int(features.shape[0]), _stream(d)))  # fmt: skip
+            else:
+                if out.dtype != torch.float32 or out.device != d:
+                    raise RuntimeError("strided forward needs a float32 tensor on the plan's device")
+                _check(self.lib.gw_forward_strided(self.handle, _ptr(features, torch.float32, d), ctypes.c_void_p(out.data_ptr()),
+                                                   int(out_ld), int(features.shape[0]), _stream(d)))  # fmt: skip
 
     def encoder_forward(self, features, x_out):
         d = self.device

@@ -848,7 +848,7 @@ static int ensure_rows_e(gw_plan* p, size_t floats) {
   return p->rows_e.alloc(floats);
 }
 
-static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const float* start, int start_ld, float* out, int nb,
+static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const float* start, int start_ld, float* out, int out_ld, int nb,
                          cudaStream_t st) {
   const gw_dims& d = p->d;
   const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = d.n_mesh, Ed = d.n_dec_edges, No = d.n_out;
@@ -936,7 +936,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
             c2.layer[0] = tc_layer(p->tc_dec_out.w2, &m, 2, false, false);
             if (start && d.residual_dim > 0)
               c2.layer[0].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
-            tc_out(c2.layer[0], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
+            tc_out(c2.layer[0], out + (size_t)s0 * No * out_ld, out_ld, d.out_dim);
             c2.n_layers = 1;
             GW_TRY(run_chain(p, c2, st));
             continue;
@@ -944,7 +944,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
           ch.layer[5] = tc_layer(p->tc_dec_out.w2, &m, 2, false, false);
           if (start && d.residual_dim > 0)
             ch.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
-          tc_out(ch.layer[5], out + (size_t)s0 * No * d.out_dim, d.out_dim, d.out_dim);
+          tc_out(ch.layer[5], out + (size_t)s0 * No * out_ld, out_ld, d.out_dim);
           ch.n_layers = 6;
           GW_TRY(run_chain(p, ch, st));
           continue;
@@ -959,7 +959,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
         GemmOp fo = first_op(No, 1, src_stream(xg + (size_t)b * No * Dn, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
         RowSrc res;
         if (start && d.residual_dim > 0) res = src_stream(start + (size_t)(s0 + b) * No * start_ld, start_ld, d.out_dim, No);
-        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)(s0 + b) * No * d.out_dim, d.out_dim, st));
+        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)(s0 + b) * No * out_ld, out_ld, st));
       }
       continue;
     }
@@ -991,7 +991,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
       GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
       RowSrc res;
       if (start && d.residual_dim > 0) res = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
-      GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * d.out_dim, d.out_dim, st));
+      GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * out_ld, out_ld, st));
     }
   }
   return 0;
@@ -1275,17 +1275,22 @@ int gw_decoder_forward(gw_plan* p, const float* x_in, const float* start, int32_
   GW_CHECK(p->d.residual_dim == 0 || (start && start_ld >= p->d.residual_dim), "start features required (decoder.py:93)");
   cudaStream_t st = (cudaStream_t)stream;
   if (gw::is_tc(p)) GW_TRY(gw::raw_bound(p, gw::SL_XIN, x_in, (long long)batch * p->d.n_mesh * p->d.node_dim, st));
-  return gw::stage_decoder(p, x_in, gw::SL_XIN, start, start_ld, out, batch, st);
+  return gw::stage_decoder(p, x_in, gw::SL_XIN, start, start_ld, out, p->d.out_dim, batch, st);
 }
 
 int gw_forward(gw_plan* p, const float* features, float* out, int32_t batch, void* stream) {
+  return gw_forward_strided(p, features, out, p ? p->d.out_dim : 0, batch, stream);
+}
+
+int gw_forward_strided(gw_plan* p, const float* features, float* out, int32_t out_ld, int32_t batch, void* stream) {
   GW_TRY(gw::check_ready(p, batch, gw::NEED_ENC | gw::NEED_PROC | gw::NEED_DEC));
   GW_CHECK(features && out, "null argument");
+  GW_CHECK(out_ld >= p->d.out_dim, "out_ld must be at least out_dim");
   cudaStream_t st = (cudaStream_t)stream;
   // x lives in xbuf0 between stages
   GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, gw::sl(p, gw::SL_X0), batch, st));
   GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, gw::SL_X0, gw::SL_X0, batch, st));
-  return gw::stage_decoder(p, p->xbuf0.p, gw::SL_X0, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, batch, st);
+  return gw::stage_decoder(p, p->xbuf0.p, gw::SL_X0, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, out_ld, batch, st);
 }
 
 int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {

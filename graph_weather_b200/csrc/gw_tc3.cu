@@ -82,7 +82,7 @@ constexpr int WSPLIT = 4;                       // worker warps per TMEM lane qu
 constexpr int WORKER_WARPS = 4 * WSPLIT, NUM_WORKERS = 32 * WORKER_WARPS;
 constexpr int WARP_PRODUCER = WORKER_WARPS, WARP_MMA = WORKER_WARPS + 1;
 constexpr int NUM_THREADS = NUM_WORKERS + 128;  // + one auxiliary warpgroup: producer, MMA issuer, two idle warps
-constexpr int WORKER_REGS = 112, AUX_REGS = 48;  // setmaxnreg: 512 x 112 + 128 x 48 = 63488 of 65536 registers
+constexpr int WORKER_REGS = 104, AUX_REGS = 56;  // setmaxnreg moves registers inside the CTA's launch allocation only (640 x 96): 512 x 104 + 128 x 56 = 60416 <= 61440.  (112 / 48 needs 63488: the workers' setmaxnreg.inc then never completes -- round-2 deadlock)
 constexpr int PAR_LAYERS = 6;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = A_SLOTS * A_SLOT_BYTES;

@@ -26,6 +26,7 @@ import torch
 from torch import nn
 
 from . import _capi, graphs, h3lite
+from .constraint import GridMapping, PhysicalConstraintLayer
 
 try:  # the reference mixes this into both wrappers (forecast.py:61, analysis.py:52)
     from huggingface_hub import PyTorchModelHubMixin
@@ -541,8 +542,6 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
                  use_checkpointing: bool = False, constraint_type: str = "none", use_thermalizer: bool = False,
                  precision: str = "auto"):  # fmt: skip
         super().__init__()
-        if constraint_type != "none":
-            raise NotImplementedError("constraint_type != 'none' (PhysicalConstraintLayer) is not on the accelerated path yet")
         if use_thermalizer:
             raise NotImplementedError("use_thermalizer=True is outside the accelerated path (stochastic layer)")
         lat_lons = _latlon_list(lat_lons)
@@ -553,10 +552,11 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
         if output_dim is None:
             output_dim = self.feature_dim
         self.output_dim = output_dim
-        unique_lats = sorted(set(lat for lat, _ in lat_lons))
-        unique_lons = sorted(set(lon for _, lon in lat_lons))
-        self.grid_shape = (len(unique_lats), len(unique_lons))
+        # grid shape and the node -> (row, col) mapping of forecast.py:122-129,178-192
         self.original_lat_lons = list(lat_lons)
+        self.__dict__["_grid_mapping"] = GridMapping(lat_lons)
+        self.grid_shape = self._grid_mapping.grid_shape
+        self.node_to_grid = self._grid_mapping.node_to_grid
         self.precision = precision
         self.encoder = Encoder(lat_lons=lat_lons, resolution=resolution, input_dim=feature_dim + aux_dim, output_dim=node_dim,
                                output_edge_dim=edge_dim, hidden_dim_processor_edge=hidden_dim_processor_edge,
@@ -583,23 +583,81 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
                     num_blocks=num_blocks)  # fmt: skip
         self._engine = _Engine(dims, precision)
         self._engine.graph_uploaders += [self.encoder._upload_graphs, self.decoder._upload_graphs]
+        if self.constraint_type != "none":  # forecast.py:162-170 (any other string fails at the first forward, as there)
+            self.constraint = PhysicalConstraintLayer(model=self, grid_shape=self.grid_shape, constraint_type=constraint_type,
+                                                      upsampling_factor=1)  # fmt: skip
 
     def _named(self):
         return [(k, v) for k, v in self.state_dict(keep_vars=True).items()]
 
-    def forward(self, features: torch.Tensor, t: int = 0) -> torch.Tensor:
+    def graph_to_grid(self, graph_tensor: torch.Tensor) -> torch.Tensor:
+        """[B, N, C] -> [B, C, H, W] (forecast.py:194-203)."""
+        return self._grid_mapping.graph_to_grid(graph_tensor)
+
+    def grid_to_graph(self, grid_tensor: torch.Tensor) -> torch.Tensor:
+        """[B, C, H, W] -> [B, N, C] (forecast.py:205-213)."""
+        return self._grid_mapping.grid_to_graph(grid_tensor)
+
+    def _check_features(self, features):
         if features.device.type != "cuda":
             _no_host_path("GraphWeatherForecaster.forward")
         if features.shape[-1] < self.feature_dim or self.output_dim != self.feature_dim:
             # the reference fails at `out + start_features` (decoder.py:93) when output_dim != feature_dim
             raise RuntimeError(f"output_dim ({self.output_dim}) must equal feature_dim ({self.feature_dim}) for the residual add")
+
+    def _constrain(self, out, f):
+        """forecast.py:231-246: the decoder output, read as a row-major H x W grid, is corrected against the input's first
+        feature_dim channels.  `rearrange(x, "b (h w) c -> b c h w")` only re-labels rows here: no layout pass exists."""
+        H, W = self.grid_shape
+        if out.shape[1] != H * W:
+            raise RuntimeError(f"Shape mismatch, can't divide axis of length {out.shape[1]} in chunks of {W}")  # einops' failure
+        cell, _ = self._grid_mapping.tensors(out.device)
+        return self.constraint.apply_rows(out, f, cell.to(torch.int32).contiguous(), self.feature_dim)
+
+    def forward(self, features: torch.Tensor, t: int = 0) -> torch.Tensor:
+        self._check_features(features)
         B = features.shape[0]
         plan = self._engine.ensure(features.device, B, self._named())
         f = features.detach().to(torch.float32).contiguous()
         out = torch.empty((B, self.decoder.num_latlons, self.output_dim), dtype=torch.float32, device=f.device)
         plan.forward(f, out)
+        if self.constraint_type != "none":
+            out = self._constrain(out, f)
         _maybe_check(plan)
         return out
+
+    @torch.no_grad()
+    def rollout(self, features: torch.Tensor, steps: int, aux=None, return_all: bool = True):
+        """Autoregressive forecast: state_{t+1} = model([state_t | aux_t]) for `steps` steps (the loop every user of the
+        reference writes around forecast.py:215-247; the reference has no helper for it).
+
+        features [B, N, feature_dim + aux_dim] is step 0's input.  `aux` is None (the auxiliary columns of `features` are
+        kept for every step), a tensor [steps, B, N, aux_dim] / [B, N, aux_dim], or a callable t -> [B, N, aux_dim].
+        Every step writes its forecast straight into the first feature_dim columns of the next step's input rows
+        (gw_forward_strided): no concatenation pass, no host round trip.  Returns [steps, B, N, feature_dim] (or the last
+        state if return_all is False)."""
+        self._check_features(features)
+        B, N, Fin = features.shape
+        plan = self._engine.ensure(features.device, B, self._named())
+        bufs = [features.detach().to(torch.float32).contiguous().clone(), None]
+        bufs[1] = bufs[0].clone()  # aux columns are present in both from the start
+        outs = torch.empty((steps if return_all else 1, B, N, self.output_dim), dtype=torch.float32, device=features.device)
+        for t in range(steps):
+            cur, nxt = bufs[t & 1], bufs[(t + 1) & 1]
+            if aux is not None and Fin > self.feature_dim:
+                a = aux(t) if callable(aux) else (aux[t] if aux.dim() == 4 else aux)
+                cur[..., self.feature_dim :] = a.to(cur.dtype)
+            if self.constraint_type == "none":
+                plan.forward(cur, nxt, out_ld=Fin)  # forecast lands in nxt[..., :feature_dim]
+                state = nxt[..., : self.output_dim]
+            else:
+                tmp = torch.empty((B, N, self.output_dim), dtype=torch.float32, device=cur.device)
+                plan.forward(cur, tmp)
+                state = self._constrain(tmp, cur)
+                nxt[..., : self.output_dim] = state
+            outs[t if return_all else 0] = state
+        _maybe_check(plan)
+        return outs if return_all else outs[0]
 
 
 @dataclass

@@ -99,6 +99,11 @@ int gw_plan_set_weights(gw_plan* plan, const gw_param* params, int32_t n, void* 
  *   features [batch, n_in, in_dim]  ->  out [batch, n_out, out_dim];  batch <= max_batch.                     */
 int gw_forward(gw_plan* plan, const float* features, float* out, int32_t batch, void* stream);
 
+/* gw_forward with a caller-chosen row stride of `out` (floats, >= out_dim): an autoregressive rollout lets step t write its
+ * forecast straight into the first out_dim columns of step t+1's feature rows (out = next_features, out_ld = in_dim), so
+ * no concatenation pass exists between steps. */
+int gw_forward_strided(gw_plan* plan, const float* features, float* out, int32_t out_ld, int32_t batch, void* stream);
+
 /* Stage entry points (the reference's sub-module API, tests/test_model.py:106-119):
  *   gw_encoder_forward   Encoder.forward   encoder.py:153-242        features -> x [batch*n_mesh, node_dim]
  *   gw_processor_forward Processor.forward processor.py:83-128       x -> x   (in place allowed)
@@ -156,6 +161,22 @@ int gw_timing_read(gw_plan* plan, int64_t* launches, double* milliseconds, void*
 int64_t gw_loss_workspace_bytes(void);
 int gw_normalized_mse_loss_sum(const float* pred, const float* target, const float* inv_variance, const float* node_weight,
                                int64_t batch, int64_t n_nodes, int32_t n_features, double* sum_out, void* workspace, void* stream);
+
+/* PhysicalConstraintLayer.forward (graph_weather/models/layers/constraint_layer.py:58-188) as GraphWeatherForecaster applies
+ * it (forecast.py:231-246: upsampling_factor 1, one patch = the whole grid), on graph-ordered rows:
+ *   hr  [batch, n_nodes, channels]      the decoder output;  lr [batch, n_nodes, lr_ld] its first lr_channels columns are the
+ *   low-resolution reference (channel c of hr pairs with channel c % lr_channels: forecast.py:243-245);
+ *   src [n_nodes] int32: the row that the reference's graph_to_grid / grid_to_graph round trip leaves at node n
+ *   (forecast.py:178-213; the identity for a complete row-major grid);  out [batch, n_nodes, channels].
+ * type: GW_CONSTRAINT_ADDITIVE y = hr + lr - mean(hr); _MULTIPLICATIVE y = hr * mean(lr) / (mean(hr) + 1e-8);
+ * _SOFTMAX y = exp(f hr) * (lr * (1 / exp(f hr))).  Means run over the nodes, per sample and channel, deterministically.
+ * workspace: gw_constraint_workspace_bytes(batch, channels) device bytes. */
+#define GW_CONSTRAINT_ADDITIVE 1
+#define GW_CONSTRAINT_MULTIPLICATIVE 2
+#define GW_CONSTRAINT_SOFTMAX 3
+int64_t gw_constraint_workspace_bytes(int64_t batch, int32_t channels);
+int gw_constraint_apply(int32_t type, const float* hr, const float* lr, int32_t lr_ld, int32_t lr_channels, const int32_t* src,
+                        float* out, int64_t batch, int64_t n_nodes, int32_t channels, float exp_factor, void* workspace, void* stream);
 
 /* Counters for bench.py: kernels launched by this library on the calling thread since the last reset. */
 int64_t gw_launch_count(void);

@@ -137,11 +137,57 @@ def run_loss(name="loss_5deg"):
     print(name, vals)
 
 
+def run_constraints(R, name="forecaster_constraints_10deg_b2"):
+    """GraphWeatherForecaster with each PhysicalConstraintLayer type (forecast.py:162-170,231-246; constraint_layer.py), the
+    reference's own code.  The layer back-references the model as a sub-module, so the reference's state_dict() recurses
+    without end: weights are loaded per sub-module.  A second, irregular case exercises the grid mapping's truncation
+    (forecast.py:178-192): latitudes that are not evenly spaced, so two nodes share a cell and others stay empty."""
+    out = {}
+    lat_lons = grid(10)
+    sd = weights.make_state_dict(weights.forecaster_shapes(), 6)
+    x = weights.make_features(2, len(lat_lons), 102, 6)
+    for ctype in ("additive", "multiplicative", "softmax"):
+        model = R.GraphWeatherForecaster(lat_lons, constraint_type=ctype).eval()
+        for sub in ("encoder", "processor", "decoder"):
+            getattr(model, sub).load_state_dict({k[len(sub) + 1:]: v for k, v in sd.items() if k.startswith(sub + ".")})
+        with torch.no_grad():
+            out[ctype] = model(x).numpy()
+        print(name, ctype, "mean|out|", float(np.abs(out[ctype]).mean()))
+    # mapping quirks: 4 x 6 grid whose latitudes are unevenly spaced
+    lats, lons = [-80.0, -75.0, 10.0, 80.0], [0.0, 50.0, 130.0, 200.0, 290.0, 350.0]
+    ll2 = [(a, b) for a in lats for b in lons]
+    m2 = R.GraphWeatherForecaster(ll2, constraint_type="additive", feature_dim=4, aux_dim=0, output_dim=4).eval()
+    rng = np.random.Generator(np.random.PCG64(9))
+    g = torch.from_numpy(rng.standard_normal((2, len(ll2), 3)).astype(np.float32))
+    grid_t = m2.graph_to_grid(g)
+    back = m2.grid_to_graph(grid_t)
+    hr = torch.from_numpy(rng.standard_normal((2, len(ll2), 3)).astype(np.float32))
+    lr = torch.from_numpy(rng.standard_normal((2, len(ll2), 3)).astype(np.float32))
+    layer_out = {}
+    for ctype in ("additive", "multiplicative", "softmax"):
+        layer = R.GraphWeatherForecaster(ll2, constraint_type=ctype, feature_dim=4, aux_dim=0, output_dim=4).constraint
+        with torch.no_grad():
+            layer_out[ctype + "_graph"] = layer(hr, lr).numpy()  # 3D (graph) inputs
+            layer_out[ctype + "_grid"] = layer(layer.model.graph_to_grid(hr), layer.model.graph_to_grid(lr)).numpy()  # 4D inputs
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), config=json.dumps(dict(step=10, batch=2, seed=6, lats=lats, lons=lons)),
+        additive=out["additive"], multiplicative=out["multiplicative"], softmax=out["softmax"],
+        node_to_grid=np.array(m2.node_to_grid, dtype=np.int64), map_in=g.numpy(), map_grid=grid_t.numpy(), map_back=back.numpy(),
+        hr=hr.numpy(), lr=lr.numpy(), **layer_out)  # fmt: skip
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     R = ref_shims.load_reference()
-    for n, s in CASES.items():
-        run_forecaster(R, n, s)
-    run_assimilator(R)
-    run_graphcast(R)
-    run_loss()
+    only = sys.argv[1:]
+    if not only or "forecaster" in only:
+        for n, s in CASES.items():
+            run_forecaster(R, n, s)
+    if not only or "assimilator" in only:
+        run_assimilator(R)
+    if not only or "graphcast" in only:
+        run_graphcast(R)
+    if not only or "loss" in only:
+        run_loss()
+    if not only or "constraints" in only:
+        run_constraints(R)
