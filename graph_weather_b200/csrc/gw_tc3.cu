@@ -571,60 +571,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     const bool l0_g0 = src_gathered(ch.layer[0].add[0].kind), l0_g1 = src_gathered(ch.layer[0].add[1].kind);
 
     // ---- stage 0, lean path: NC0 + NC1 64-column chunks from one or two aligned sources, fully unrolled ------------------------
-    auto stage0_fast = [&](auto NC0c, auto NC1c, int tile) {
+    // The rows stream from HBM (edge state) or L2 (node state): up to four chunks (16 x LDG.128 per thread) are in flight before
+    // the first one is converted, so a tile pays the memory latency once, not once per chunk.  GBR: the operand is
+    // relu(gathered row + broadcast row); the two tables are kept apart until the chunk is converted (two chunks in flight).
+    auto stage0_fast = [&](auto NC0c, auto NC1c, auto GBRc, int tile) {
       constexpr int NC0 = decltype(NC0c)::value, NC1 = decltype(NC1c)::value, NC = NC0 + NC1;
+      constexpr bool GBR = decltype(GBRc)::value != 0;
+      constexpr int DEPTH = GBR ? 2 : 4;
       const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
       const int nvalid = min(TILE_M, rows - i0);
       int rl[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
-      const char* pa[4];
-      const char* pb[4] = {nullptr, nullptr, nullptr, nullptr};
-      const char* pc[4] = {nullptr, nullptr, nullptr, nullptr};
-      row_ptrs(ch.a0[0], bs, i0, rl, cofs, pa);
-      const bool gbr = ch.a0[0].kind == SRC_GATHER_BCAST_RELU;
-      if (gbr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pc[k] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + rl[k]) * (size_t)ch.a0[0].ld2 + cofs);
-      }
-      if constexpr (NC1 > 0) row_ptrs(ch.a0[1], bs, i0, rl, cofs, pb);
-      auto fetch = [&](auto cc, float (&o)[16]) {
-        constexpr int c = decltype(cc)::value;
-        if (ABL3(ABL_LOADS)) return;
-        if constexpr (c < NC0) {
-          ldfrag4(pa, 256 * c, o);
-          if (gbr) {
-            float t[16];
-            ldfrag4(pc, 256 * c, t);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + t[i], 0.f);
-          }
-        } else {
-          ldfrag4(pb, 256 * (c - NC0), o);
-        }
-      };
-      float buf[2][16] = {};
-      fetch(ic<0>{}, buf[0]);
+      // gather rows of layer 0's addends: requested first, parked in shared memory once the operand loads are under way
+      uint32_t g0[4] = {0u, 0u, 0u, 0u}, g1[4] = {0u, 0u, 0u, 0u};
       if (l0_add0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = l0_g0 ? (uint32_t)__ldg(ch.layer[0].add[0].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
+        for (int k = 0; k < 4; ++k) g0[k] = l0_g0 ? (uint32_t)__ldg(ch.layer[0].add[0].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
       }
       if (l0_add1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
+        for (int k = 0; k < 4; ++k) g1[k] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
+      }
+      const char* pa[4];
+      const char* pb[4] = {nullptr, nullptr, nullptr, nullptr};  // second source, or the broadcast table of GBR
+      row_ptrs(ch.a0[0], bs, i0, rl, cofs, pa);
+      if constexpr (GBR) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pb[k] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + rl[k]) * (size_t)ch.a0[0].ld2 + cofs);
+      } else if constexpr (NC1 > 0) {
+        row_ptrs(ch.a0[1], bs, i0, rl, cofs, pb);
+      }
+      float buf[DEPTH][16] = {};
+      float bufb[GBR ? DEPTH : 1][16] = {};
+      auto fetch = [&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        if (ABL3(ABL_LOADS)) return;
+        if constexpr (GBR) {
+          ldfrag4(pa, 256 * c, buf[c % DEPTH]);
+          ldfrag4(pb, 256 * c, bufb[c % DEPTH]);
+        } else if constexpr (c < NC0) {
+          ldfrag4(pa, 256 * c, buf[c % DEPTH]);
+        } else {
+          ldfrag4(pb, 256 * (c - NC0), buf[c % DEPTH]);
+        }
+      };
+      static_for<0, (NC < DEPTH ? NC : DEPTH)>([&](auto cc) { fetch(cc); });
+      if (l0_add0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = g0[k];
+      }
+      if (l0_add1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = g1[k];
       }
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        if constexpr (c + 1 < NC) fetch(ic<c + 1>{}, buf[(c + 1) & 1]);
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
         if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
-        float(&cur)[16] = buf[c & 1];
+        float(&cur)[16] = buf[c % DEPTH];
+        if constexpr (GBR) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = fmaxf(cur[i] + bufb[c % DEPTH][i], 0.f);
+        }
         if (a0scale != 1.f) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
         }
         if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
         publish(slot);
+        if constexpr (c + DEPTH < NC) fetch(ic<c + DEPTH>{});  // refill the buffer just consumed
         tr.ev(500 + c);
       });
       fi += NC;
@@ -680,6 +696,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       }
       if constexpr (has_add1) {
         if (ld_on) ldfrag4(p1, 0, pf1);
+      }
+      // targets of my rows (fused per-target sums): requested before the accumulator wait / the statistics pass
+      int dseg[4] = {0, 0, 0, 0}, dprev_q = 0;
+      if constexpr (has_seg) {
+        const int32_t* sd = L.seg_dst + i0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dseg[k] = (re[k] < nvalid) ? __ldg(sd + re[k]) : -1 - k;
+        dprev_q = (lr == 0 && i0 + 32 * q > 0 && 32 * q < nvalid) ? __ldg(sd + 32 * q - 1) : -1 - 7;
       }
       if (!waited) {
         tr.ev(600 + l);
@@ -770,14 +794,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       float c1f = 0.f, c2f = 0.f;
       char* tail_p = nullptr;
       char* head_p = nullptr;
-      int dseg[4] = {0, 0, 0, 0};
       bool b0 = false;
       if constexpr (has_seg) {
-        const int32_t* sd = L.seg_dst + i0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dseg[k] = (re[k] < nvalid) ? __ldg(sd + re[k]) : -1 - k;
         int dprev = __shfl_up_sync(0xffffffffu, dseg[3], 4);
-        if (lr == 0) dprev = (i0 + 32 * q > 0 && 32 * q < nvalid) ? __ldg(sd + 32 * q - 1) : -1 - 7;
+        if (lr == 0) dprev = dprev_q;
         b0 = dseg[0] != dprev, b1 = dseg[1] != dseg[0], b2 = dseg[2] != dseg[1], b3 = dseg[3] != dseg[2];
         const bool in123 = b1 || b2 || b3;
         const uint32_t nb0 = __shfl_down_sync(0xffffffffu, (uint32_t)b0, 4), nin = __shfl_down_sync(0xffffffffu, (uint32_t)in123, 4);
@@ -945,9 +965,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           const int t = l < 0 ? tile : next_tile;
           if (t < num_tiles) {
             if constexpr (MODE == 1) {
-              if (ch.a0[1].kind != SRC_NONE) stage0_fast(ic<4>{}, ic<4>{}, t);          // node chains: [x | aggregate]
-              else if (ch.K0 == 256) stage0_fast(ic<4>{}, ic<0>{}, t);                  // edge chains, products of x
-              else stage0_fast(ic<2>{}, ic<0>{}, t);                                    // widened feature rows (K0 = 128)
+              if (ch.a0[1].kind != SRC_NONE) stage0_fast(ic<4>{}, ic<4>{}, ic<0>{}, t);  // node chains: [x | aggregate]
+              else if (ch.a0[0].kind == SRC_GATHER_BCAST_RELU) stage0_fast(ic<4>{}, ic<0>{}, ic<1>{}, t);  // decoder edges
+              else if (ch.K0 == 256) stage0_fast(ic<4>{}, ic<0>{}, ic<0>{}, t);          // edge chains, products of x
+              else stage0_fast(ic<2>{}, ic<0>{}, ic<0>{}, t);                            // widened feature rows (K0 = 128)
             } else {
               stage0(t);
             }
@@ -1247,6 +1268,7 @@ static void tc3_mark_lean(TcChain& ch) {
     const bool two = ch.a0[1].kind != SRC_NONE;
     ok = ok && ch.a0[0].kind != SRC_NONE && wsum == ch.K0;
     ok = ok && (two ? (ch.a0[0].width == 256 && ch.a0[1].width == 256) : (ch.K0 == 256 || ch.K0 == 128));
+    if (ch.a0[0].kind == SRC_GATHER_BCAST_RELU) ok = ok && !two && ch.K0 == 256;
     if (ok) ch.fast |= (int32_t)0x80000000u;
   }
   static const int kinds4[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,

@@ -147,7 +147,7 @@ def run_constraints(R, name="forecaster_constraints_10deg_b2"):
     sd = weights.make_state_dict(weights.forecaster_shapes(), 6)
     x = weights.make_features(2, len(lat_lons), 102, 6)
     for ctype in ("additive", "multiplicative", "softmax"):
-        model = R.GraphWeatherForecaster(lat_lons, constraint_type=ctype).eval()
+        model = R.GraphWeatherForecaster(lat_lons, constraint_type=ctype)  # (.eval() recurses through the layer's back-reference; no dropout anyway)
         for sub in ("encoder", "processor", "decoder"):
             getattr(model, sub).load_state_dict({k[len(sub) + 1:]: v for k, v in sd.items() if k.startswith(sub + ".")})
         with torch.no_grad():
@@ -156,7 +156,7 @@ def run_constraints(R, name="forecaster_constraints_10deg_b2"):
     # mapping quirks: 4 x 6 grid whose latitudes are unevenly spaced
     lats, lons = [-80.0, -75.0, 10.0, 80.0], [0.0, 50.0, 130.0, 200.0, 290.0, 350.0]
     ll2 = [(a, b) for a in lats for b in lons]
-    m2 = R.GraphWeatherForecaster(ll2, constraint_type="additive", feature_dim=4, aux_dim=0, output_dim=4).eval()
+    m2 = R.GraphWeatherForecaster(ll2, constraint_type="additive", feature_dim=4, aux_dim=0, output_dim=4)
     rng = np.random.Generator(np.random.PCG64(9))
     g = torch.from_numpy(rng.standard_normal((2, len(ll2), 3)).astype(np.float32))
     grid_t = m2.graph_to_grid(g)
