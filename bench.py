@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=["auto", "fp32", "fp32_simt", "bf16"],
                     help="default: auto at 1 deg (the constructor default: fp32-faithful tcgen05), bf16 at 0.25 deg (configs[2])")  # fmt: skip
     ap.add_argument("--boundary", default="gather", choices=["gather", "gather_sync", "loss"], help="what crosses GPUs at the loss boundary (N > 1)")
+    ap.add_argument("--gather-mode", default="auto", choices=["auto", "fused", "fused_peer", "p2p_copy", "nccl"],
+                    help="transport of the gather boundary: fused into the forecast's last kernel (NVLink multicast / peer stores), copy engines, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle comparison of this run's output")
     a = ap.parse_args()
@@ -312,7 +314,7 @@ def main():
     x_host = torch.randn(a.batch, n, FIN).pin_memory()
     x = x_host.to(dev)
     out_host = torch.empty(a.batch, n, FOUT).pin_memory()
-    gather = BoundaryGather(world * a.batch, dev) if (world > 1 and a.boundary != "loss") else None
+    gather = BoundaryGather(world * a.batch, dev, mode=a.gather_mode) if (world > 1 and a.boundary != "loss") else None
     crit = target = None
     if world > 1 and a.boundary == "loss":
         crit = NormalizedMSELoss([1.0] * FOUT, [tuple(p) for p in np.asarray(lat_lons).tolist()], normalize=False)
@@ -325,8 +327,15 @@ def main():
             return crit(y, target, total_batch=world * a.batch)  # one all-reduced scalar
         return gather(y, overlap=(a.boundary == "gather"))
 
+    def forward_boundary(inp):
+        """One step: the forward and whatever crosses GPUs at the loss boundary.  With the gather boundary the transfer is
+        part of the forward's last kernel (BoundaryGather mode "fused") wherever symmetric memory is available."""
+        if gather is not None:
+            return gather.forward(model, inp, overlap=(a.boundary == "gather"))
+        return boundary(model(inp))
+
     def step_resident():
-        return boundary(model(x))
+        return forward_boundary(x)
 
     # End-to-end step through the public module call: every step copies its inputs in from pinned host memory and its
     # forecast back out.  The copies run on their own streams (double-buffered), so step i+1's input upload and step
@@ -334,7 +343,7 @@ def main():
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     x_bufs = [torch.empty_like(x), torch.empty_like(x)]
     out_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
-    e2e_state = {"i": 0, "used": [None, None]}
+    e2e_state = {"i": 0, "used": [None, None], "dl": [None, None]}
 
     def step_e2e():
         i = e2e_state["i"]
@@ -348,14 +357,23 @@ def main():
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
         cur.wait_event(ev_in)
-        y = model(x_bufs[b])
-        boundary(y)
+        if gather is not None:  # the gather buffer about to be written was downloaded two steps ago: that copy must be done
+            kb = gather._i & 1
+            if e2e_state["dl"][kb] is not None:
+                cur.wait_event(e2e_state["dl"][kb])
+        y = forward_boundary(x_bufs[b])
+        if gather is not None:  # this rank's own rows of the gathered forecast are what it downloads
+            y = y[rank * a.batch : (rank + 1) * a.batch]
         ev_c = torch.cuda.Event()
         ev_c.record(cur)
         e2e_state["used"][b] = ev_c
         s_out.wait_event(ev_c)
         with torch.cuda.stream(s_out):
             out_bufs[b].copy_(y, non_blocking=True)
+            if gather is not None:
+                ev_d = torch.cuda.Event()
+                ev_d.record(s_out)
+                e2e_state["dl"][kb] = ev_d
         y.record_stream(s_out)
         return y
 
@@ -409,6 +427,9 @@ def main():
     cfg["workload"] = f"{a.grid}_grid_{n_pts}pts_102to78_batch{a.batch}_per_gpu_{'bf16' if resolved == 'bf16' else 'fp32'}"
     cfg["precision"] = {"requested": a.precision, "resolved": resolved}
     cfg["plan_gib"] = round(plan.device_bytes() / 2**30, 2)
+    if gather is not None:
+        cfg["boundary_transport"] = {"mode": gather.mode, "fused_store": (gather._fused[0][0] if getattr(gather, "_fused", None) else None),
+                                     "fallback_reason": gather.fallback_reason}  # fused_store 1 = NVLink multicast, 2 = peer stores
 
     # parity of THIS run: one sample of the bench's own batch against the CPU oracle (1 deg; checker only, outside any timing)
     parity = None

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "gw_plan_destroy": (ctypes.c_int, [_vp]),
     "gw_plan_device_bytes": (_i64, [_vp]),
     "gw_plan_set_encoder_graph": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "gw_plan_set_h3_tables": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp]),
+    "gw_plan_build_obs_graph": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "gw_plan_set_latent_graph": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "gw_plan_set_decoder_graph": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "gw_plan_set_weights": (ctypes.c_int, [_vp, ctypes.POINTER(GwParam), _i32, _vp]),
@@ -63,6 +65,7 @@ _SIGNATURES = {
     "gw_timing_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double), _vp]),
     "gw_loss_workspace_bytes": (_i64, []),
     "gw_normalized_mse_loss_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "gw_plan_set_output_peers": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(_i64)]),
     "gw_forward_strided": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "gw_constraint_workspace_bytes": (_i64, [_i64, _i32]),
     "gw_constraint_apply": (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, ctypes.c_float, _vp, _vp]),
@@ -171,6 +174,28 @@ class Plan:
                                                       _ptr(pt, torch.int32, d), _ptr(at, torch.float32, d), _stream(d)))  # fmt: skip
             torch.cuda.current_stream(d).synchronize()  # the temporaries above are freed on return
 
+    def set_h3_tables(self, tab: dict):
+        """Uploads h3lite.device_tables(res) for the device-side observation graph (gw_plan_build_obs_graph)."""
+        d = self.device
+        H = int(tab["n_cells"])
+        fr = self._dev(tab["frames"], torch.float64)
+        co = self._dev(tab["cell_of"], torch.int32)
+        slot = self._dev(H - 1 - tab["rank"], torch.int32)
+        la, ln = self._dev(tab["cell_lat"], torch.float64), self._dev(tab["cell_lng"], torch.float64)
+        with torch.cuda.device(d):
+            _check(self.lib.gw_plan_set_h3_tables(self.handle, int(tab["res"]), H, int(tab["lattice_n"]), _ptr(fr, torch.float64, d),
+                                                  _ptr(co, torch.int32, d), _ptr(slot, torch.int32, d), _ptr(la, torch.float64, d),
+                                                  _ptr(ln, torch.float64, d), float(tab["scale"]), float(tab["rot_cos"]), float(tab["rot_sin"]),
+                                                  _stream(d)))  # fmt: skip
+            torch.cuda.current_stream(d).synchronize()  # the temporaries above are freed on return
+
+    def build_obs_graph(self, lat_lon_heights):
+        """[n_obs, 3] float32 (lat deg, lon deg, height) on the plan's device -> the encoder graph, built on the device."""
+        d = self.device
+        with torch.cuda.device(d):
+            _check(self.lib.gw_plan_build_obs_graph(self.handle, _ptr(lat_lon_heights, torch.float32, d), int(lat_lon_heights.shape[0]),
+                                                    _stream(d)))  # fmt: skip
+
     def set_latent_graph(self, src, dst, ptr, attr):
         d = self.device
         s, t, p = (self._dev(a, torch.int32) for a in (src, dst, ptr))
@@ -241,6 +266,11 @@ class Plan:
             ld = int(start.shape[-1]) if start is not None else 0
             _check(self.lib.gw_decoder_forward(self.handle, _ptr(x_in, torch.float32, d), sp, ld, _ptr(out, torch.float32, d),
                                                int(batch), _stream(d)))  # fmt: skip
+
+    def set_output_peers(self, mode: int, deltas=()):
+        """Fused loss-boundary gather (gw_plan_set_output_peers): mode 0 off, 1 multicast alias, 2 peer mappings."""
+        arr = (_i64 * max(1, len(deltas)))(*[int(v) for v in deltas])
+        _check(self.lib.gw_plan_set_output_peers(self.handle, int(mode), len(deltas), arr))
 
     def status(self) -> int:
         """Synchronising read of the device status word (0 = ok); raises on a non-zero status."""

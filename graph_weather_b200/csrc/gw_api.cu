@@ -142,9 +142,17 @@ struct gw_plan {
   // fused per-target sums (gw_tc3.cu F_SEG): target of every decoder edge, carry rows of segments cut by a tile quadrant
   DevBuf<int32_t> dec_dst;
   DevBuf<float> seg_carry;
-  DevBuf<int> deg_stats;
-  int enc_maxdeg = 0, lat_maxdeg = 0, lat_mindeg = 0, dec_maxdeg = 0, dec_mindeg = 0;
+  DevBuf<int> deg_stats, enc_deg;  // {longest, shortest} segment: scratch for host reads; the encoder graph's stays on the device
+  int lat_maxdeg = 0, lat_mindeg = 0, dec_maxdeg = 0, dec_mindeg = 0;
+  // H3 tables for the device-side observation graph (gw_graph.cu): plan-owned copies
+  DevBuf<double> h3_frames, h3_lat, h3_lng;
+  DevBuf<int32_t> h3_cell_of, h3_slot;
+  DevBuf<unsigned char> obs_ws;
+  gw::H3Tables h3;
   bool fuse_seg = true;
+  // loss-boundary gather fused into the forecast chain (gw_plan_set_output_peers): byte offsets from `out` to its aliases
+  int out_mode = 0, n_out_peers = 0;
+  long long out_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // optional per-launch CUDA-event timing (gw_timing_*): events are recorded on the launching stream
   bool timing = false;
   int cur_tag = 0;
@@ -650,7 +658,8 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, float*
           GW_CUDA(launch_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->agg_mesh.p, De, st));
         }
         ch.a0[0] = bounded(src_bcast(p->xm0.p, Dn, Dn), sl(p, SL_XM0));
-        ch.a0[1] = bounded(src_stream(p->agg_mesh.p, De, De, H), sl(p, SL_ROWS_E), (float)std::max(p->enc_maxdeg, 1));
+        ch.a0[1] = bounded(src_stream(p->agg_mesh.p, De, De, H), sl(p, SL_ROWS_E));
+        ch.a0[1].bound_mul_i = p->enc_deg.p;  // a sum of up to (longest lat/lon -> mesh segment) rows
         ch.K0 = Dn + De;
         const Mlp& m = p->enc_blk_node;
         ch.layer[0] = tc_layer(p->tc_enc_mnode.w0, &m, 0, true, true);
@@ -841,6 +850,15 @@ static ProcGraph latent_graph_of(gw_plan* p) {
 }
 
 // AssimilatorDecoder.forward (assimilator_decoder.py:173-200) + Decoder residual (decoder.py:92-94).
+// multi-GPU loss boundary: the chain that stores the forecast also stores it into every GPU's gather buffer (gw_tc3.cu out_mode)
+static void apply_out_peers(gw_plan* p, TcChain& ch) {
+  if (p->out_mode == 0) return;
+  char* o = reinterpret_cast<char*>(ch.layer[ch.n_layers - 1].out);
+  ch.out_mode = p->out_mode, ch.n_out_peers = p->n_out_peers;
+  if (p->out_mode == 1) ch.out_mc = reinterpret_cast<float*>(o + p->out_delta[0]);
+  for (int j = 0; j < p->n_out_peers && j < 8; ++j) ch.out_peer[j] = reinterpret_cast<float*>(o + p->out_delta[j]);
+}
+
 // e' rows of the decoder block are only materialised by the CUDA-core path and by the unfused fallback: allocated on demand
 static int ensure_rows_e(gw_plan* p, size_t floats) {
   if (p->rows_e.n >= floats) return 0;
@@ -854,6 +872,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
   const int Dn = d.node_dim, De = d.edge_dim, He = d.hidden_edge, H = d.n_mesh, Ed = d.n_dec_edges, No = d.n_out;
   RowSrc none;
   const bool fuse = is_tc(p) && p->fuse_seg && p->dec_maxdeg >= 1 && p->dec_maxdeg <= 8;
+  GW_CHECK(p->out_mode == 0 || (is_tc(p) && p->tc_dec_out_ok), "the fused loss-boundary gather needs the tensor-core output chain");
   if (!fuse) GW_TRY(ensure_rows_e(p, (size_t)p->chunk * std::max((size_t)p->d.n_in, (size_t)Ed) * De));
   for (int s0 = 0; s0 < nb; s0 += p->chunk) {
     const int cb = std::min(p->chunk, nb - s0);
@@ -938,6 +957,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
               c2.layer[0].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
             tc_out(c2.layer[0], out + (size_t)s0 * No * out_ld, out_ld, d.out_dim);
             c2.n_layers = 1;
+            apply_out_peers(p, c2);
             GW_TRY(run_chain(p, c2, st));
             continue;
           }
@@ -946,6 +966,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
             ch.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
           tc_out(ch.layer[5], out + (size_t)s0 * No * out_ld, out_ld, d.out_dim);
           ch.n_layers = 6;
+          apply_out_peers(p, ch);
           GW_TRY(run_chain(p, ch, st));
           continue;
         }
@@ -1006,6 +1027,14 @@ static int csr_stats(gw_plan* p, const int32_t* ptr, int n, int32_t* dst, int* m
   GW_CUDA(cudaMemcpyAsync(got, p->deg_stats.p, sizeof(got), cudaMemcpyDeviceToHost, st));
   GW_CUDA(cudaStreamSynchronize(st));
   *maxdeg = got[0], *mindeg = n > 0 ? got[1] : 0;
+  return 0;
+}
+
+// longest lat/lon -> mesh segment of the current encoder graph, left on the device (it scales a magnitude bound): no sync
+static int encoder_degree(gw_plan* p, cudaStream_t st) {
+  static const int init[2] = {0, 0x7fffffff};
+  GW_CUDA(cudaMemcpyAsync(p->enc_deg.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  GW_CUDA(launch_csr_expand(p->enc_ptr.p, p->d.n_mesh, nullptr, p->enc_deg.p, st));
   return 0;
 }
 
@@ -1097,7 +1126,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->lat_src.alloc(d.n_lat_edges) | p->lat_dst.alloc(d.n_lat_edges) | p->lat_ptr.alloc(d.n_mesh + 1);
   rc |= p->lat_attr.alloc((size_t)d.n_lat_edges * 2);
   rc |= p->dec_src.alloc(d.n_dec_edges) | p->dec_ptr.alloc(d.n_out + 1) | p->dec_attr.alloc((size_t)d.n_dec_edges * 2);
-  rc |= p->dec_dst.alloc(d.n_dec_edges) | p->deg_stats.alloc(2) | p->bounds.alloc(gw::SL_COUNT);
+  rc |= p->dec_dst.alloc(d.n_dec_edges) | p->deg_stats.alloc(2) | p->enc_deg.alloc(2) | p->bounds.alloc(gw::SL_COUNT);
   rc |= p->zeros_h3.alloc((size_t)d.n_mesh * d.in_dim);
   rc |= p->e_enc.alloc((size_t)d.n_in * De) | p->xm0.alloc((size_t)d.n_mesh * Dn) | p->C1_enc.alloc((size_t)d.n_in * He);
   rc |= p->e_lat.alloc((size_t)d.n_lat_edges * De) | p->e_dec.alloc((size_t)d.n_dec_edges * De);
@@ -1144,7 +1173,8 @@ int gw_plan_destroy(gw_plan* p) {
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
   p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release(), p->agg_grid.release();
-  p->bounds.release(), p->dec_dst.release(), p->seg_carry.release(), p->deg_stats.release();
+  p->bounds.release(), p->dec_dst.release(), p->seg_carry.release(), p->deg_stats.release(), p->enc_deg.release();
+  p->h3_frames.release(), p->h3_lat.release(), p->h3_lng.release(), p->h3_cell_of.release(), p->h3_slot.release(), p->obs_ws.release();
   if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1176,10 +1206,51 @@ int gw_plan_set_encoder_graph(gw_plan* p, int32_t n_in, const int32_t* enc_mesh,
   GW_CUDA(cudaMemcpyAsync(p->enc_attr.p, attr, (size_t)n_in * p->d.enc_edge_attr_dim * 4, cudaMemcpyDeviceToDevice, st));
   p->n_in_cur = n_in;
   p->have_enc = true;
-  {
-    int mn = 0;
-    GW_TRY(gw::csr_stats(p, p->enc_ptr.p, p->d.n_mesh, nullptr, &p->enc_maxdeg, &mn, st));
-  }
+  GW_TRY(gw::encoder_degree(p, st));
+  if (p->w_enc) GW_TRY(gw::precompute_encoder_constants(p, st));  // per-call graphs (assimilator_encoder.py:118)
+  return 0;
+}
+
+int gw_plan_set_h3_tables(gw_plan* p, int32_t res, int32_t n_cells, int32_t lattice_n, const double* face_frames, const int32_t* cell_of,
+                          const int32_t* cell_slot, const double* cell_lat, const double* cell_lng, double scale, double rot_cos,
+                          double rot_sin, void* stream) {
+  GW_CHECK(p && face_frames && cell_of && cell_slot && cell_lat && cell_lng, "null argument");
+  GW_CHECK(n_cells == p->d.n_mesh, "the H3 tables must describe the plan's mesh (n_cells == n_mesh)");
+  GW_CHECK(lattice_n > 0 && res >= 0, "bad table sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  const size_t w = 2 * (size_t)lattice_n + 1;
+  GW_TRY(p->h3_frames.alloc(180));
+  GW_TRY(p->h3_cell_of.alloc(20 * w * w));
+  GW_TRY(p->h3_slot.alloc(n_cells));
+  GW_TRY(p->h3_lat.alloc(n_cells));
+  GW_TRY(p->h3_lng.alloc(n_cells));
+  GW_CUDA(cudaMemcpyAsync(p->h3_frames.p, face_frames, 180 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->h3_cell_of.p, cell_of, 20 * w * w * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->h3_slot.p, cell_slot, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->h3_lat.p, cell_lat, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  GW_CUDA(cudaMemcpyAsync(p->h3_lng.p, cell_lng, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  gw::H3Tables& t = p->h3;
+  t.res = res, t.n_cells = n_cells, t.lat_n = lattice_n;
+  t.frames = p->h3_frames.p, t.cell_of = p->h3_cell_of.p, t.cell_slot = p->h3_slot.p, t.cell_lat = p->h3_lat.p, t.cell_lng = p->h3_lng.p;
+  t.scale = scale, t.cr = rot_cos, t.sr = rot_sin;
+  return 0;
+}
+
+int gw_plan_build_obs_graph(gw_plan* p, const float* lat_lon_heights, int32_t n_obs, void* stream) {
+  GW_CHECK(p && lat_lon_heights, "null argument");
+  GW_CHECK(p->h3.res >= 0, "gw_plan_set_h3_tables must be called first");
+  GW_CHECK(p->d.enc_edge_attr_dim == 3, "the observation graph carries 3 edge attributes (sin d, cos d, height)");
+  GW_CHECK(n_obs >= 1 && n_obs <= p->d.n_in, "n_obs exceeds the plan's capacity (gw_dims.n_in)");
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_CUDA(cudaSetDevice(p->device));
+  const size_t need = gw::obs_graph_workspace_bytes(p->d.n_in);
+  if (p->obs_ws.n < need) GW_TRY(p->obs_ws.alloc(need));
+  GW_CUDA(gw::launch_obs_graph(p->h3, lat_lon_heights, n_obs, p->d.n_mesh, p->enc_mesh.p, p->enc_perm.p, p->enc_ptr.p, p->enc_attr.p,
+                               p->obs_ws.p, p->obs_ws.n, p->tc_status_dev, st));
+  p->n_in_cur = n_obs;
+  p->have_enc = true;
+  GW_TRY(gw::encoder_degree(p, st));
   if (p->w_enc) GW_TRY(gw::precompute_encoder_constants(p, st));  // per-call graphs (assimilator_encoder.py:118)
   return 0;
 }
@@ -1291,6 +1362,14 @@ int gw_forward_strided(gw_plan* p, const float* features, float* out, int32_t ou
   GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, gw::sl(p, gw::SL_X0), batch, st));
   GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, gw::SL_X0, gw::SL_X0, batch, st));
   return gw::stage_decoder(p, p->xbuf0.p, gw::SL_X0, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, out_ld, batch, st);
+}
+
+int gw_plan_set_output_peers(gw_plan* p, int32_t mode, int32_t n, const int64_t* deltas_bytes) {
+  GW_CHECK(p != nullptr, "null plan");
+  GW_CHECK(mode == 0 || (mode == 1 && n == 1 && deltas_bytes) || (mode == 2 && n >= 1 && n <= 8 && deltas_bytes), "bad mode / count");
+  p->out_mode = mode, p->n_out_peers = mode == 2 ? n : 0;
+  for (int j = 0; j < 8; ++j) p->out_delta[j] = (mode != 0 && j < n) ? deltas_bytes[j] : 0;
+  return 0;
 }
 
 int gw_latent_edge_features(gw_plan* p, float* edge_attr_out, void* stream) {

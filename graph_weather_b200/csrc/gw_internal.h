@@ -31,4 +31,19 @@ cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, f
                                 cudaStream_t stream);  // perm16: feature order of gw_tc3.cu (gw_pack.cu)
 cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream);
 
+// device-side observation graph of the assimilator (gw_graph.cu)
+struct H3Tables {
+  int res = -1, n_cells = 0, lat_n = 0;  // lattice table covers a, b in [-lat_n, lat_n]
+  const double* frames = nullptr;        // [20][9]: face centre c, in-plane unit vectors ex, ey
+  const int32_t* cell_of = nullptr;      // [20][(2 lat_n + 1)^2]: canonical cell of lattice point (a, b) on the face, -1 if none
+  const int32_t* cell_slot = nullptr;    // [n_cells]: mesh-node slot of the cell in the encoder's numbering (H - 1 - rank)
+  const double* cell_lat = nullptr;      // [n_cells] radians (as the host path sees them: through degrees and back)
+  const double* cell_lng = nullptr;
+  double scale = 0.0, cr = 1.0, sr = 0.0;  // plane -> lattice scale; Class III rotation (cos, sin), identity for even res
+};
+
+size_t obs_graph_workspace_bytes(int n);
+cudaError_t launch_obs_graph(const H3Tables& t, const float* llh, int n, int n_slots, int32_t* slot, int32_t* perm, int32_t* ptr, float* attr,
+                             void* ws, size_t ws_bytes, int32_t* status, cudaStream_t st);
+
 }  // namespace gw

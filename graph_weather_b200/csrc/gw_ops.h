@@ -35,6 +35,7 @@ struct RowSrc {
   const int32_t* perm = nullptr;  // optional edge permutation for SEGSUM
   const float* bound2 = nullptr;  // SRC_GATHER_BCAST_RELU: bound of base2
   float bound_mul = 1.f;          // the source's values are bounded by *bound * bound_mul (e.g. sums of up to bound_mul rows)
+  const int32_t* bound_mul_i = nullptr;  // ... times this device integer when set (segment lengths known only on the device)
   const float* bound = nullptr;   // device float: |values of this source| <= *bound (null: unknown).  Tensor-core chains use it
                                   // to scale fp16-split operands into range (gw_tc3.cu, "operand range")
 };
@@ -102,6 +103,13 @@ struct TcChain {
   long long* trace = nullptr; // optional debug timeline: [8 roles][1024 events][2] = {clock64, code}; CTA 0 only
   int32_t fast = 0;           // gw_tc3: bit l = layer l takes the lean full-width path, bit 31 = stage 0 does (set by the launcher)
   int32_t ablate = 0;         // diagnostics build only (-DGW_ABLATE): bit mask of pipeline parts to skip, for timing attribution
+  // Loss-boundary gather fused into the chain that produces the forecast (multi-GPU; graph_weather_b200/dist.py): the LAST layer's
+  // fp32 result rows are stored, tile by tile as they leave the accumulator, into the gather buffers of every GPU of the job --
+  // out_mode 1: one multimem.st per value to the NVLink multicast alias of `out` (the switch replicates it to every GPU);
+  // out_mode 2: one plain store per peer mapping.  The aliases address the same element as the layer's `out`.
+  int32_t out_mode = 0, n_out_peers = 0;
+  float* out_mc = nullptr;
+  float* out_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   TcLayer layer[TC_MAX_LAYERS];
 };
 

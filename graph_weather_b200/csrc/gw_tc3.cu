@@ -296,7 +296,11 @@ __device__ __forceinline__ float range_scale(float m) {
   return __uint_as_float((uint32_t)(127 + 14 - e) << 23);         // 2^(14-e)   (e <= 127 -> exponent field >= 14: normal)
 }
 __device__ __forceinline__ float ldbound(const float* p) { return p ? __ldg(p) : 0.f; }
-__device__ __forceinline__ float srcbound(const RowSrc& s) { return s.bound ? __ldg(s.bound) * s.bound_mul : 0.f; }
+__device__ __forceinline__ float srcbound(const RowSrc& s) {
+  if (!s.bound) return 0.f;
+  const float m = __ldg(s.bound) * s.bound_mul;
+  return s.bound_mul_i ? m * (float)max(__ldg(s.bound_mul_i), 1) : m;
+}
 
 // MODE 0: every part takes the general path; 1: every part takes the lean full-width path.  (A third mode that chose per
 // part inside one kernel was measured slower than the general path: the live state of both paths spills.)
@@ -634,11 +638,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] = fmaxf(cur[i] + bufb[c % DEPTH][i], 0.f);
         }
-        if (a0scale != 1.f) {
+        if (a0scale != 1.f) {  // (two copies of the conversion: see layer_fast)
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
+          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
+        } else {
+          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
         }
-        if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
         publish(slot);
         if constexpr (c + DEPTH < NC) fetch(ic<c + DEPTH>{});  // refill the buffer just consumed
         tr.ev(500 + c);
@@ -931,11 +937,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         if constexpr (feeds) {
           const uint32_t slot = (fi + s) % A_SLOTS;
-          if (osc != 1.f) {
+          if (osc != 1.f) {  // range scaling active (rare).  Two copies of the conversion keep this a real, warp-uniform branch:
+                             // as a short predicated block the 16 multiplies would be issued (predicated off) in every chunk
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= osc;
+            if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
+          } else {
+            if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
           }
-          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
           publish(slot);
         }
         tr.ev(700 + 10 * l + s);
@@ -1173,12 +1182,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             if (has_out && !ABL3(ABL_STORES)) {
               float* ob = L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo + col;
               const bool inside = 64 * s + 16 * hq + 16 <= L.out_cols;  // warp-uniform
+              // where the values go: this GPU's memory, or (last layer of the forecast chain on a multi-GPU job) every GPU's gather
+              // buffer at once -- NVLink multicast or one store per peer mapping
+              const int omode = last_layer ? ch.out_mode : 0;
+              const ptrdiff_t mc_delta = reinterpret_cast<const char*>(ch.out_mc) - reinterpret_cast<const char*>(L.out);
+              auto put4 = [&](float* p, float a, float b, float c, float d) {
+                if (omode == 0) {
+                  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+                } else if (omode == 1) {
+                  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<char*>(p) + mc_delta), "f"(a), "f"(b),
+                               "f"(c), "f"(d)
+                               : "memory");
+                } else {
+                  for (int j = 0; j < ch.n_out_peers; ++j)
+                    *reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + (reinterpret_cast<const char*>(ch.out_peer[j]) - reinterpret_cast<const char*>(L.out))) =
+                        make_float4(a, b, c, d);
+                }
+              };
+              auto put2 = [&](float* p, float a, float b) {
+                if (omode == 0) {
+                  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+                } else if (omode == 1) {
+                  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(p) + mc_delta), "f"(a), "f"(b) : "memory");
+                } else {
+                  for (int j = 0; j < ch.n_out_peers; ++j)
+                    *reinterpret_cast<float2*>(reinterpret_cast<char*>(p) + (reinterpret_cast<const char*>(ch.out_peer[j]) - reinterpret_cast<const char*>(L.out))) =
+                        make_float2(a, b);
+                }
+              };
+              auto put1 = [&](float* p, float a) {
+                if (omode == 0) {
+                  *p = a;
+                } else if (omode == 1) {
+                  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<char*>(p) + mc_delta), "f"(a) : "memory");
+                } else {
+                  for (int j = 0; j < ch.n_out_peers; ++j)
+                    *reinterpret_cast<float*>(reinterpret_cast<char*>(p) + (reinterpret_cast<const char*>(ch.out_peer[j]) - reinterpret_cast<const char*>(L.out))) = a;
+                }
+              };
               if (inside && vec4_ok(ob - col, L.ldo)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (re[k] < nvalid) {
                     const int i = 8 * (k >> 1) + 2 * (k & 1);
-                    *reinterpret_cast<float4*>(ob + (size_t)re[k] * (size_t)L.ldo) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
+                    put4(ob + (size_t)re[k] * (size_t)L.ldo, v[i], v[i + 1], v[i + 4], v[i + 5]);
                   }
                 }
               } else if (inside && vec2_ok(ob - col, L.ldo)) {
@@ -1187,8 +1234,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
                   if (re[k] < nvalid) {
                     float* orow = ob + (size_t)re[k] * (size_t)L.ldo;
                     const int i = 8 * (k >> 1) + 2 * (k & 1);
-                    *reinterpret_cast<float2*>(orow) = make_float2(v[i], v[i + 1]);
-                    *reinterpret_cast<float2*>(orow + 2) = make_float2(v[i + 4], v[i + 5]);
+                    put2(orow, v[i], v[i + 1]);
+                    put2(orow + 2, v[i + 4], v[i + 5]);
                   }
                 }
               } else {
@@ -1199,8 +1246,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1), c = col + 2 * j;
-                      if (c < L.out_cols) orow[2 * j] = v[i];
-                      if (c + 1 < L.out_cols) orow[2 * j + 1] = v[i + 1];
+                      if (c < L.out_cols) put1(orow + 2 * j, v[i]);
+                      if (c + 1 < L.out_cols) put1(orow + 2 * j + 1, v[i + 1]);
                     }
                   }
                 }
@@ -1349,7 +1396,8 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   if (getenv("GW_TC3_NOFAST")) ch.fast = 0;
   const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
   // (mode 2, per-part selection inside one kernel, measured slower than the general path: both paths' live state spills)
-  const int mode = ch.fast == all ? 1 : 0;
+  int mode = ch.fast == all ? 1 : 0;
+  if (ch.out_mode != 0) mode = 0;  // the multi-GPU boundary stores live in the general path's store tiers
   if (mode == 0)
     for (int l = 0; l < ch.n_layers; ++l)
       if (ch.layer[l].seg_dst) return cudaErrorInvalidValue;  // the fused per-target sum exists on the lean path only

@@ -6,6 +6,11 @@ weights / graphs are replicated, and the only communication is ONE gather of the
 (they hold every SM with 227 KB of shared memory, so an NCCL kernel issued beside them only runs in the gaps between
 them and stalls the statically scheduled tiles of the next kernel -- measured in round 1: no overlap at all):
 
+  * mode "fused"     `gather.forward(model, features)`: the chain kernel that produces the forecast stores every tile of it, as it
+                     leaves the tensor cores, into the gather buffer of EVERY GPU -- one multimem.st per value to the NVLink
+                     multicast alias of the symmetric buffer (the NVSwitch replicates it), or one store per peer mapping where
+                     multicast is unavailable (csrc/gw_tc3.cu out_mode, gw_plan_set_output_peers).  Compute and collective are one
+                     kernel; two symmetric-memory barriers (a few microseconds) order it.  No separate transfer exists.
   * mode "p2p_copy"  every rank owns a symmetric-memory gather buffer (torch symmetric memory: cuMem allocations mapped
                      into every peer over NVLink).  A rank's shard is pushed into each peer's buffer by the COPY ENGINES
                      (device-to-device cudaMemcpyAsync into the peer mapping, no kernel), on a side stream, followed by the
@@ -80,22 +85,29 @@ class BoundaryGather:
         if self.device.type != "cuda":
             self.mode = "gloo"
             return
-        if want in ("auto", "p2p_copy"):
+        if want in ("auto", "fused", "fused_peer", "p2p_copy"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
                 pg = self.group if self.group is not None else dist.group.WORLD
-                self._bufs, self._hdl, self._peers = [], [], []
+                self._bufs, self._hdl, self._peers, self._fused = [], [], [], []
                 for _ in range(2):
                     t = symm_mem.empty(shape, dtype=y.dtype, device=self.device)
                     h = symm_mem.rendezvous(t, pg)
                     self._bufs.append(t)
                     self._hdl.append(h)
                     self._peers.append([h.get_buffer(r, shape, y.dtype) for r in range(self.world)])
-                self.mode = "p2p_copy"
+                    # aliases of this rank's buffer for the in-kernel stores: (mode, byte deltas from the local address)
+                    ptrs = [int(v) for v in h.buffer_ptrs]
+                    mc = int(getattr(h, "multicast_ptr", 0) or 0)
+                    if mc and want != "fused_peer" and self.world <= 8:
+                        self._fused.append((1, [mc - ptrs[self.rank]]))
+                    elif self.world <= 8:
+                        self._fused.append((2, [ptrs[r] - ptrs[self.rank] for r in range(self.world)]))
+                self.mode = "p2p_copy" if want == "p2p_copy" or len(self._fused) != 2 else "fused"
                 return
             except Exception as e:  # no symmetric memory on this box / build: NCCL on the side stream
-                if want == "p2p_copy":
+                if want != "auto":
                     raise
                 self.fallback_reason = f"{type(e).__name__}: {e}"
         self._bufs = [torch.empty(shape, dtype=y.dtype, device=self.device) for _ in range(2)]
@@ -108,6 +120,34 @@ class BoundaryGather:
             self._setup(y)
         if self.mode == "gloo":
             return all_gather_batch(y, self.total, self.group)
+        if self.mode == "fused":  # called with a finished tensor: the copy-engine path moves it (same buffers)
+            return self._copy_gather(y, overlap)
+        return self._copy_gather(y, overlap)
+
+    def forward(self, model, features: torch.Tensor, overlap: bool = True) -> torch.Tensor:
+        """model(features) on this rank's shard, gathered over all ranks: [total_batch, N, F].  In mode "fused" the forward
+        itself writes into every GPU's gather buffer (no transfer after it); otherwise forward, then the gather."""
+        if self._bufs is None and self.mode not in ("gloo",):
+            B, N = features.shape[0], features.shape[1]
+            self._setup(torch.empty((B, N, model.output_dim), dtype=torch.float32, device=features.device))
+        if self.mode != "fused":
+            return self(model(features), overlap=overlap)
+        a, b = self.ranges[self.rank]
+        assert features.shape[0] == b - a, "local shard does not match shard_range"
+        k = self._i & 1
+        self._i += 1
+        h = self._hdl[k]
+        mode, deltas = self._fused[k]
+        h.barrier(channel=0)  # every rank has finished with buffer k (its use two calls ago) before anybody stores into it
+        model.forward_into(features, self._bufs[k][a:b], peers=(mode, deltas))
+        h.barrier(channel=1)  # the stores of every rank have landed in every buffer
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._done[k] = ev
+        return self._bufs[k]
+
+    def _copy_gather(self, y: torch.Tensor, overlap: bool = True) -> torch.Tensor:
+        a, b = self.ranges[self.rank]
         k = self._i & 1
         self._i += 1
         cur = torch.cuda.current_stream(self.device)
@@ -118,7 +158,7 @@ class BoundaryGather:
         self.side.wait_event(ready)
         y = y.contiguous()
         with torch.cuda.stream(self.side):
-            if self.mode == "p2p_copy":
+            if self.mode in ("p2p_copy", "fused"):
                 h = self._hdl[k]
                 h.barrier(channel=0)  # every rank is past the forward of this step: nobody still reads buffer k
                 for d in range(self.world):  # own slot first, then the peers in ring order (spreads the NVSwitch ports)

@@ -420,3 +420,30 @@ def haversine_rads(lat1, lng1, lat2, lng2):
 def table(res: int) -> _ResTable:
     """Cached per-resolution cell table (centres, neighbours, index order)."""
     return _table(res)
+
+
+def device_tables(res: int):
+    """The arrays gw_plan_set_h3_tables uploads for the device-side point location (csrc/gw_graph.cu mirrors `_ResTable.locate`):
+    face frames [20, 9] (centre, i-axis, j-axis), the per-face lattice table cell_of [20, 2n+1, 2n+1] (canonical cell of lattice
+    point (a, b) on the face, -1 where no cell lies), cell centres as `graphs._sincos_attr` sees them (radians taken through
+    degrees and back), and the plane -> lattice transform (scale, rotation cos / sin)."""
+    t = _table(res)
+    c, ex, ey = _faces()
+    frames = np.concatenate([c, ex, ey], axis=1).astype(np.float64)
+    n = int(math.ceil(2.0 * (_SQRT7**res) * 2.0 / math.sqrt(3.0))) + 2
+    aa, bb = np.meshgrid(np.arange(-n, n + 1), np.arange(-n, n + 1), indexing="ij")
+    px, py = _lattice_to_plane(aa.ravel(), bb.ravel(), res)
+    spacing = _RES0_U_GNOMONIC / (_SQRT7**res)
+    cell_of = np.full((20, (2 * n + 1) ** 2), -1, dtype=np.int32)
+    for f in range(20):
+        vec = _face_plane_to_vec(np.full(px.shape, f), px, py)
+        dist, cell = t.tree.query(vec, k=1)
+        ok = dist <= 0.25 * spacing  # the same acceptance test as `locate`
+        cell_of[f, ok] = cell[ok]
+    rot = _class3(res)
+    return dict(
+        res=res, n_cells=t.num, lattice_n=n, frames=frames, cell_of=cell_of.reshape(20, 2 * n + 1, 2 * n + 1),
+        cell_lat=np.radians(np.degrees(t.lat)), cell_lng=np.radians(np.degrees(t.lng)),
+        scale=(_SQRT7**res) / _RES0_U_GNOMONIC, rot_cos=math.cos(_M_AP7_ROT_RADS) if rot else 1.0, rot_sin=math.sin(_M_AP7_ROT_RADS) if rot else 0.0,
+        rank=t.rank.astype(np.int64),
+    )  # fmt: skip

@@ -467,11 +467,18 @@ class AssimilatorEncoder(nn.Module):
     def _upload_graphs(self, plan):
         m = self._g_lat
         plan.set_latent_graph(m.src, m.dst, m.ptr, m.edge_attr[m.perm])
+        plan.set_h3_tables(h3lite.device_tables(self.resolution))  # for the device-side observation graph
 
     def _upload_obs(self, engine, plan, lat_lon_heights):
         """The reference rebuilds the observation graph on every forward (assimilator_encoder.py:118,170-216).  Here the
         upload is skipped only when the observation set is provably the same: the key is the CONTENT of lat_lon_heights
         (it is copied to the host to build the graph anyway) plus the engine's plan generation, never a tensor address."""
+        if lat_lon_heights.is_cuda and os.environ.get("GW_B200_HOST_OBS_GRAPH", "0") != "1":
+            # the observation graph is rebuilt ON THE DEVICE for every call, as the reference rebuilds it for every call
+            # (assimilator_encoder.py:118): point location, edge attributes, slot-sorted CSR -- no host copy, no synchronisation
+            plan.build_obs_graph(lat_lon_heights.detach().to(device=plan.device, dtype=torch.float32).contiguous())
+            self._obs_key = None
+            return
         llh = lat_lon_heights.detach().to(device="cpu", dtype=torch.float64).contiguous().numpy()
         key = (engine.generation, llh.shape, hash(llh.tobytes()))
         if key != self._obs_key:
@@ -623,6 +630,29 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
         plan.forward(f, out)
         if self.constraint_type != "none":
             out = self._constrain(out, f)
+        _maybe_check(plan)
+        return out
+
+    def forward_into(self, features: torch.Tensor, out: torch.Tensor, peers=None) -> torch.Tensor:
+        """forward(features) written into a caller-provided [B, N, output_dim] tensor.  `peers` = (mode, byte deltas) makes the
+        chain that produces the forecast store it into every GPU's gather buffer as well (gw_plan_set_output_peers;
+        graph_weather_b200.dist.BoundaryGather passes the aliases of its symmetric buffers): the multi-GPU loss-boundary gather,
+        fused with the last GEMM.  Not available with a constraint layer (its correction follows the forecast)."""
+        self._check_features(features)
+        if self.constraint_type != "none":
+            raise NotImplementedError("forward_into: the constraint layer post-processes the forecast; gather its output instead")
+        B = features.shape[0]
+        if tuple(out.shape) != (B, self.decoder.num_latlons, self.output_dim) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise RuntimeError("forward_into: `out` must be a contiguous float32 [B, N, output_dim] tensor")
+        plan = self._engine.ensure(features.device, B, self._named())
+        f = features.detach().to(torch.float32).contiguous()
+        if peers is not None:
+            plan.set_output_peers(peers[0], peers[1])
+        try:
+            plan.forward(f, out, out_ld=self.output_dim)
+        finally:
+            if peers is not None:
+                plan.set_output_peers(0)
         _maybe_check(plan)
         return out
 

@@ -82,6 +82,21 @@ int64_t gw_plan_device_bytes(const gw_plan* plan);
  *   decoder : edges grouped by output point: src[j] mesh slot, ptr[n_out+1]; attr [Ed,2]                      */
 int gw_plan_set_encoder_graph(gw_plan* plan, int32_t n_in, const int32_t* enc_mesh, const int32_t* perm,
                               const int32_t* ptr, const float* attr, void* stream);
+/* Device-side construction of the assimilator's per-call observation graph
+ * (AssimilatorEncoder.create_input_graph, assimilator_encoder.py:170-216: h3.latlng_to_cell + great_circle_distance per
+ * observation in a Python loop).  gw_plan_set_h3_tables uploads, once, the hexagonal-grid tables of the plan's resolution
+ * (all DEVICE pointers, copied): face_frames [20][9] = centre, i-axis, j-axis unit vectors of every icosahedron face;
+ * cell_of [20][(2 lattice_n + 1)^2] = canonical cell of each face-lattice point or -1; cell_slot [n_cells] = mesh slot of the
+ * cell (H-1-rank, the encoder's numbering, encoder.py:80-84); cell_lat / cell_lng [n_cells] radians; scale, rot_cos,
+ * rot_sin: gnomonic plane -> lattice transform of the resolution.  gw_plan_build_obs_graph then replaces
+ * gw_plan_set_encoder_graph for every forward: lat_lon_heights [n_obs, 3] fp32 degrees / degrees / height on the device ->
+ * mesh slot, [sin d, cos d, height] edge attributes, slot-sorted permutation and CSR inside the plan; no host copy, no
+ * synchronisation. */
+int gw_plan_set_h3_tables(gw_plan* plan, int32_t res, int32_t n_cells, int32_t lattice_n, const double* face_frames, const int32_t* cell_of,
+                          const int32_t* cell_slot, const double* cell_lat, const double* cell_lng, double scale, double rot_cos,
+                          double rot_sin, void* stream);
+int gw_plan_build_obs_graph(gw_plan* plan, const float* lat_lon_heights, int32_t n_obs, void* stream);
+
 int gw_plan_set_latent_graph(gw_plan* plan, const int32_t* src, const int32_t* dst, const int32_t* ptr,
                              const float* attr, void* stream);
 int gw_plan_set_decoder_graph(gw_plan* plan, const int32_t* src, const int32_t* ptr, const float* attr, void* stream);
@@ -103,6 +118,18 @@ int gw_forward(gw_plan* plan, const float* features, float* out, int32_t batch, 
  * forecast straight into the first out_dim columns of step t+1's feature rows (out = next_features, out_ld = in_dim), so
  * no concatenation pass exists between steps. */
 int gw_forward_strided(gw_plan* plan, const float* features, float* out, int32_t out_ld, int32_t batch, void* stream);
+
+/* Multi-GPU loss boundary fused into the forecast's last chain (the one gather of the outputs).  After this call
+ * every gw_forward / gw_forward_strided / gw_decoder_forward stores its `out` rows, as the tiles leave the tensor cores, into
+ * the gather buffers of every GPU of the job as well:
+ *   mode 1  NVLink multicast: deltas_bytes[0] = (multicast alias of the caller's gather buffer) - (its local address); one
+ *           multimem.st per value, the NVSwitch replicates it to all GPUs of the multicast group (this GPU included);
+ *   mode 2  peer stores: deltas_bytes[j] = (mapping of GPU j's gather buffer in this process) - (local address), n <= 8 entries
+ *           (this GPU's own buffer included): one store per GPU and value;
+ *   mode 0  off (default).
+ * `out` passed to the forward must lie inside the local gather buffer the deltas were taken from.  The caller orders the
+ * exchange with its own cross-GPU barrier (graph_weather_b200/dist.py).  Tensor-core precisions only. */
+int gw_plan_set_output_peers(gw_plan* plan, int32_t mode, int32_t n, const int64_t* deltas_bytes);
 
 /* Stage entry points (the reference's sub-module API, tests/test_model.py:106-119):
  *   gw_encoder_forward   Encoder.forward   encoder.py:153-242        features -> x [batch*n_mesh, node_dim]
@@ -127,7 +154,7 @@ int gw_latent_edge_features(gw_plan* plan, float* edge_attr_out, void* stream);
 /* Synchronises `stream` and returns (then clears) the plan's device status word: 0 = ok;
  * bit 0: an activation left the fp16 range in GW_PREC_FP32_TC (results invalid: rerun with GW_PREC_FP32_SIMT);
  * bit 1: internal pipeline timeout; bit 2: shared-memory misalignment; bit 3: a magnitude bound overflowed (inf / nan
- * inputs).  Non-zero must be treated as failure.  (Operands are range-scaled from rigorous per-tensor magnitude bounds, so
+ * inputs); bit 4: an observation could not be located on the mesh (non-finite coordinates).  Non-zero must be treated as failure.  (Operands are range-scaled from rigorous per-tensor magnitude bounds, so
  * bit 0 is a guard that finite inputs cannot trip.) */
 int gw_plan_status(gw_plan* plan, int32_t* status_out, void* stream);
 /* Non-blocking read of the same word (it lives in host-mapped memory): reflects every kernel that has COMPLETED so far

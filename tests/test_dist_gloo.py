@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from graph_weather_b200.dist import all_gather_batch, max_over_ranks, shard_range
+from graph_weather_b200.dist import BoundaryGather, all_gather_batch, max_over_ranks, shard_range
 
 
 def _free_port():
@@ -22,7 +22,11 @@ def _worker(rank, world, port, total, q):
     full = torch.arange(total * 3 * 2, dtype=torch.float32).reshape(total, 3, 2)
     got = all_gather_batch(full[a:b] * 1.0, total)
     mx = max_over_ranks(10.0 + rank, "cpu")
-    q.put((rank, bool(torch.equal(got, full)), mx))
+    # the loss-boundary object the bench and training loops use: on CPU tensors it is the gloo all-gather, same interface
+    gather = BoundaryGather(total, "cpu")
+    got2 = gather(full[a:b] * 1.0)
+    gather.wait()
+    q.put((rank, bool(torch.equal(got, full)) and bool(torch.equal(got2, full)) and gather.mode == "gloo", mx))
     dist.destroy_process_group()
 
 
@@ -77,8 +81,9 @@ def _loss_worker(rank, world, port, q):
     crit.local_sum = cpu_local_sum
     a, b = shard_range(total, rank, world)
     got = float(crit(pred[a:b], target[a:b], group=dist.group.WORLD, total_batch=total))
+    got_derived = float(crit(pred[a:b], target[a:b], group=dist.group.WORLD))  # global batch derived from the shards
     ref = float(restate.normalized_mse_loss(pred, target, var, lat_lons, True))
-    q.put((rank, abs(got - ref) <= 1e-6 * abs(ref), got))
+    q.put((rank, abs(got - ref) <= 1e-6 * abs(ref) and abs(got_derived - ref) <= 1e-6 * abs(ref), got))
     dist.destroy_process_group()
 
 
