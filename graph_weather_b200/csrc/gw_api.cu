@@ -149,6 +149,10 @@ struct gw_plan {
   DevBuf<int32_t> h3_cell_of, h3_slot;
   DevBuf<unsigned char> obs_ws;
   gw::H3Tables h3;
+  // chunk table + partial sums of the encoder's two-level segment sum (gw_simt.cu)
+  DevBuf<int32_t> enc_chunk_seg, enc_chunk_j0, enc_seg_chunk0;
+  DevBuf<float> enc_partial;
+  int enc_max_chunks = 0;
   bool fuse_seg = true;
   // loss-boundary gather fused into the forecast chain (gw_plan_set_output_peers): byte offsets from `out` to its aliases
   int out_mode = 0, n_out_peers = 0;
@@ -655,7 +659,11 @@ static int stage_encoder(gw_plan* p, const float* features, float* x_out, float*
         ch.rows_per_sample = H, ch.batch = cb;
         {  // the lat/lon -> mesh segments are very skewed (a polar cell collects thousands of points): reduced by their own kernel
           TimedLaunch t(p, st);
-          GW_CUDA(launch_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->agg_mesh.p, De, st));
+          if (De == 256 && p->enc_partial.p)
+            GW_CUDA(launch_segsum_chunked(eprime, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->enc_chunk_seg.p, p->enc_chunk_j0.p,
+                                          p->enc_seg_chunk0.p, p->enc_max_chunks, p->enc_partial.p, p->agg_mesh.p, De, st));
+          else
+            GW_CUDA(launch_segsum(eprime, De, De, p->enc_ptr.p, p->enc_perm.p, N, H, cb, p->agg_mesh.p, De, st));
         }
         ch.a0[0] = bounded(src_bcast(p->xm0.p, Dn, Dn), sl(p, SL_XM0));
         ch.a0[1] = bounded(src_stream(p->agg_mesh.p, De, De, H), sl(p, SL_ROWS_E));
@@ -1035,6 +1043,8 @@ static int encoder_degree(gw_plan* p, cudaStream_t st) {
   static const int init[2] = {0, 0x7fffffff};
   GW_CUDA(cudaMemcpyAsync(p->enc_deg.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
   GW_CUDA(launch_csr_expand(p->enc_ptr.p, p->d.n_mesh, nullptr, p->enc_deg.p, st));
+  if (p->enc_chunk_seg.p)  // chunk table of the two-level segment sum follows the graph
+    GW_CUDA(launch_seg_chunks(p->enc_ptr.p, p->d.n_mesh, p->enc_chunk_seg.p, p->enc_chunk_j0.p, p->enc_seg_chunk0.p, st));
   return 0;
 }
 
@@ -1143,6 +1153,11 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->ebuf0.alloc(B * d.n_lat_edges * De) | p->ebuf1.alloc(B * d.n_lat_edges * De);
   rc |= p->P.alloc(B * d.n_mesh * 2 * He);
   rc |= p->agg_mesh.alloc(B * d.n_mesh * De);
+  if (tc && d.n_in > 0) {
+    p->enc_max_chunks = gw::seg_chunk_bound(d.n_mesh, d.n_in);
+    rc |= p->enc_chunk_seg.alloc(p->enc_max_chunks) | p->enc_chunk_j0.alloc(p->enc_max_chunks) | p->enc_seg_chunk0.alloc(d.n_mesh + 1);
+    rc |= p->enc_partial.alloc(chunk * (size_t)p->enc_max_chunks * 256);
+  }
   if (tc) {
     rc |= p->agg_grid.alloc(chunk * d.n_out * De);
     rc |= p->seg_carry.alloc(std::max(chunk * dec_tiles, B * (lat_tiles + 1)) * 1024);
@@ -1175,6 +1190,7 @@ int gw_plan_destroy(gw_plan* p) {
   p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release(), p->agg_grid.release();
   p->bounds.release(), p->dec_dst.release(), p->seg_carry.release(), p->deg_stats.release(), p->enc_deg.release();
   p->h3_frames.release(), p->h3_lat.release(), p->h3_lng.release(), p->h3_cell_of.release(), p->h3_slot.release(), p->obs_ws.release();
+  p->enc_chunk_seg.release(), p->enc_chunk_j0.release(), p->enc_seg_chunk0.release(), p->enc_partial.release();
   if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;

@@ -194,6 +194,110 @@ cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* p
   return cudaGetLastError();
 }
 
+// ---- two-level segment sum for very uneven segments (the encoder: a polar mesh cell collects thousands of lat/lon points at
+// 0.25 degree, most cells a few) ------------------------------------------------------------------------------------------
+// Segments are cut into chunks of <= SEG_CHUNK rows (chunk table built on the device by gw_seg_chunks_kernel whenever the graph
+// changes); one CTA sums one chunk with four independent row loads in flight; segments of one chunk are written straight to
+// the output, longer ones leave per-chunk partial sums that gw_segsum_finish_kernel adds in chunk order.  Deterministic; the
+// order differs from one long left-to-right sum only in where the partial sums are cut.
+constexpr int SEG_CHUNK = 64;
+// one block: every thread counts the chunks of a contiguous run of segments, a block-wide exclusive scan places them
+__global__ void __launch_bounds__(1024) gw_seg_chunks_kernel(const int32_t* __restrict__ ptr, int n_seg, int32_t* __restrict__ chunk_seg,
+                                                             int32_t* __restrict__ chunk_j0, int32_t* __restrict__ seg_chunk0) {
+  __shared__ int warp_tot[32];
+  const int t = threadIdx.x, ipt = (n_seg + 1023) / 1024;
+  const int i0 = min(t * ipt, n_seg), i1 = min(i0 + ipt, n_seg);
+  int mine = 0;
+  for (int i = i0; i < i1; ++i) mine += max(1, (ptr[i + 1] - ptr[i] + SEG_CHUNK - 1) / SEG_CHUNK);  // empty segment: one empty chunk (zeroes its row)
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int w = warp_tot[t];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (t >= o) w += v;
+    }
+    warp_tot[t] = w;
+  }
+  __syncthreads();
+  int c = incl - mine + ((t >> 5) ? warp_tot[(t >> 5) - 1] : 0);
+  for (int i = i0; i < i1; ++i) {
+    seg_chunk0[i] = c;
+    const int j0 = ptr[i], j1 = ptr[i + 1];
+    int j = j0;
+    do {
+      chunk_seg[c] = i, chunk_j0[c] = j, ++c;
+      j += SEG_CHUNK;
+    } while (j < j1);
+  }
+  if (t == 1023) seg_chunk0[n_seg] = warp_tot[31];
+}
+__global__ void __launch_bounds__(64) gw_segsum_chunk_kernel(const float* __restrict__ base, int ld, const int32_t* __restrict__ ptr,
+                                                             const int32_t* __restrict__ perm, int src_rows, int rows,
+                                                             const int32_t* __restrict__ chunk_seg, const int32_t* __restrict__ chunk_j0,
+                                                             const int32_t* __restrict__ seg_chunk0, int max_chunks, float* __restrict__ partial,
+                                                             float* __restrict__ out, int ldo) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  if (c >= __ldg(seg_chunk0 + rows)) return;
+  const int seg = __ldg(chunk_seg + c), j0 = __ldg(chunk_j0 + c), j1 = min(j0 + SEG_CHUNK, __ldg(ptr + seg + 1));
+  const float* src = base + (size_t)b * src_rows * ld + threadIdx.x * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = j0;
+  for (; j + 4 <= j1; j += 4) {
+    int e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = perm ? __ldg(perm + j + u) : j + u;
+    float4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)e[u] * ld));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc.x += t[u].x, acc.y += t[u].y, acc.z += t[u].z, acc.w += t[u].w;
+  }
+  for (; j < j1; ++j) {
+    const int e = perm ? __ldg(perm + j) : j;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)e * ld));
+    acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+  }
+  const bool single = __ldg(seg_chunk0 + seg + 1) - __ldg(seg_chunk0 + seg) == 1;
+  float* dst = single ? out + ((size_t)b * rows + seg) * ldo : partial + ((size_t)b * max_chunks + c) * 256;
+  *reinterpret_cast<float4*>(dst + threadIdx.x * 4) = acc;
+}
+__global__ void __launch_bounds__(64) gw_segsum_finish_kernel(const float* __restrict__ partial, const int32_t* __restrict__ seg_chunk0, int rows,
+                                                              int max_chunks, float* __restrict__ out, int ldo) {
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const int c0 = __ldg(seg_chunk0 + seg), c1 = __ldg(seg_chunk0 + seg + 1);
+  if (c1 - c0 <= 1) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = c0; c < c1; ++c) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)b * max_chunks + c) * 256 + threadIdx.x * 4));
+    acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)b * rows + seg) * ldo + threadIdx.x * 4) = acc;
+}
+int seg_chunk_bound(int n_seg, int n_rows) { return n_seg + (n_rows + SEG_CHUNK - 1) / SEG_CHUNK + 1; }
+cudaError_t launch_seg_chunks(const int32_t* ptr, int n_seg, int32_t* chunk_seg, int32_t* chunk_j0, int32_t* seg_chunk0, cudaStream_t st) {
+  gw_seg_chunks_kernel<<<1, 1024, 0, st>>>(ptr, n_seg, chunk_seg, chunk_j0, seg_chunk0);
+  count_launch();
+  return cudaGetLastError();
+}
+// width must be 256 (one float4 per thread of the 64-thread CTA)
+cudaError_t launch_segsum_chunked(const float* base, int ld, const int32_t* ptr, const int32_t* perm, int src_rows, int rows, int batch,
+                                  const int32_t* chunk_seg, const int32_t* chunk_j0, const int32_t* seg_chunk0, int max_chunks, float* partial,
+                                  float* out, int ldo, cudaStream_t st) {
+  if (rows <= 0 || batch <= 0) return cudaSuccess;
+  if ((ld & 3) || (ldo & 3)) return cudaErrorInvalidValue;
+  gw_segsum_chunk_kernel<<<dim3(max_chunks, batch), 64, 0, st>>>(base, ld, ptr, perm, src_rows, rows, chunk_seg, chunk_j0, seg_chunk0, max_chunks,
+                                                                partial, out, ldo);
+  gw_segsum_finish_kernel<<<dim3(rows, batch), 64, 0, st>>>(partial, seg_chunk0, rows, max_chunks, out, ldo);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
 // dst[r, 0:ld_dst] = [src[r, 0:width], 0 ...]: widens rows whose width / stride are not multiples of 64 floats (the 102
 // input features) so that the tensor-core chain can read them with aligned 128-bit loads.  The pass sees every input value,
 // so it also produces their absolute maximum (amax, may be null): the magnitude bound the chain's operand scaling starts from.

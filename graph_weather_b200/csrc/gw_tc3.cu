@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       }
       // fused per-target sums: which of my four consecutive rows start a new target, and who owns which piece
       bool b1 = false, b2 = false, b3 = false, tail_st = false, head_st = false, inner_any = false;
-      float c1f = 0.f, c2f = 0.f;
+      float c1f = 0.f, c2f = 0.f, m1f = 1.f, m2f = 1.f, m3f = 1.f;
       char* tail_p = nullptr;
       char* head_p = nullptr;
       bool b0 = false;
@@ -811,6 +811,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         const bool cont1 = lr < 7 && !nb0;                          // my last piece continues into the next thread's rows
         const bool cont2 = cont1 && !nin && lr < 6 && !nnb0;        // ... and through all of them into the one after
         c1f = cont1 ? 1.f : 0.f, c2f = cont2 ? 1.f : 0.f;
+        m1f = b1 ? 0.f : 1.f, m2f = b2 ? 0.f : 1.f, m3f = b3 ? 0.f : 1.f;
         // the piece that ends with my row 3 is mine to store if it starts inside my rows, or if I hold the first rows of the
         // quadrant (then it continues a segment of the previous quadrant / tile and goes to the carry buffer)
         const bool starts_here = b0 || in123;
@@ -910,9 +911,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             const int ci = 4 * (c >> 1) + (c & 1);
             const float x0 = v[ci], x1 = v[ci + 2], x2 = v[ci + 8], x3 = v[ci + 10];
             r0[c] = x0;
-            r1[c] = b1 ? x1 : r0[c] + x1;
-            r2[c] = b2 ? x2 : r1[c] + x2;
-            T[c] = b3 ? x3 : r2[c] + x3;
+            r1[c] = fmaf(m1f, r0[c], x1);  // m = 0 at a boundary (the running sum restarts), 1 inside a segment
+            r2[c] = fmaf(m2f, r1[c], x2);
+            T[c] = fmaf(m3f, r2[c], x3);
             H[c] = b1 ? r0[c] : (b2 ? r1[c] : (b3 ? r2[c] : T[c]));
           }
           if (head_st && !ABL3(ABL_STORES)) *reinterpret_cast<float4*>(head_p + 256 * s) = make_float4(H[0], H[1], H[2], H[3]);

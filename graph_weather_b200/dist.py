@@ -104,7 +104,10 @@ class BoundaryGather:
                         self._fused.append((1, [mc - ptrs[self.rank]]))
                     elif self.world <= 8:
                         self._fused.append((2, [ptrs[r] - ptrs[self.rank] for r in range(self.world)]))
-                self.mode = "p2p_copy" if want == "p2p_copy" or len(self._fused) != 2 else "fused"
+                # "auto" takes the copy engines: measured on 2 x B200 (profiles/r02_d_*), 1 degree / batch 8 per GPU, the transfer
+                # hides completely under the next forward (12.39 ms per step = the 1-GPU step), while the in-kernel stores of the
+                # 78-wide (312-byte, 8-byte aligned) forecast rows cost the last chain +0.8 ms (peer stores) / +1.5 ms (multicast)
+                self.mode = "fused" if want in ("fused", "fused_peer") and len(self._fused) == 2 else "p2p_copy"
                 return
             except Exception as e:  # no symmetric memory on this box / build: NCCL on the side stream
                 if want != "auto":
@@ -132,6 +135,7 @@ class BoundaryGather:
             self._setup(torch.empty((B, N, model.output_dim), dtype=torch.float32, device=features.device))
         if self.mode != "fused":
             return self(model(features), overlap=overlap)
+        # (selectable with mode="fused" / "fused_peer"; see _setup for the measured trade-off)
         a, b = self.ranges[self.rank]
         assert features.shape[0] == b - a, "local shard does not match shard_range"
         k = self._i & 1
