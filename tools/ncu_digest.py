@@ -68,8 +68,35 @@ def report(path, cmd):
         print(f"  {op:10s} {100 * c / tot:5.1f} % | {100 * samp[op] / ts:5.1f} %")
 
 
+def traffic(workload, pairs):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of the captured kernel classes, tagged with
+    the hash of the CUDA sources and the workload they were measured on (bench.py quotes the figure only when both match).
+        python tools/ncu_digest.py traffic <workload> proc_edge=gpurun_out/a.ncu-rep dec_edge=gpurun_out/b.ncu-rep > profiles/traffic.json"""
+    import json
+    import os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    out = {"source_hash": bench.source_hash(), "workload": workload, "unit": "bytes per launch (dram read + write)"}
+    for pair in pairs:
+        tag, path = pair.split("=", 1)
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        h, units, v = rows[0], rows[1], rows[-1]
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(m)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            tot += float(v[i].replace(",", "")) * scale
+        out[tag] = tot
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3:])
     else:
         report(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
