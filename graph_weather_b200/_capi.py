@@ -69,6 +69,9 @@ _SIGNATURES = {
     "gw_forward_strided": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "gw_constraint_workspace_bytes": (_i64, [_i64, _i32]),
     "gw_constraint_apply": (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, ctypes.c_float, _vp, _vp]),
+    "gw_normalized_mse_loss_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, ctypes.c_float, _vp, _vp]),
+    "gw_train_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "gw_train_backward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(GwParam), _i32, _vp]),
     "gw_launch_count": (_i64, []),
     "gw_launch_count_reset": (None, []),
 }
@@ -266,6 +269,26 @@ class Plan:
             ld = int(start.shape[-1]) if start is not None else 0
             _check(self.lib.gw_decoder_forward(self.handle, _ptr(x_in, torch.float32, d), sp, ld, _ptr(out, torch.float32, d),
                                                int(batch), _stream(d)))  # fmt: skip
+
+    def train_forward(self, features, out):
+        """Forward on the exact-fp32 plan that keeps the activations for `train_backward` (one backward per forward)."""
+        d = self.device
+        with torch.cuda.device(d):
+            _check(self.lib.gw_train_forward(self.handle, _ptr(features, torch.float32, d), _ptr(out, torch.float32, d), int(features.shape[0]),
+                                             _stream(d)))  # fmt: skip
+
+    def train_backward(self, grad_out, grad_features, named_grads):
+        """grad_out [B, N, out] -> gradients written into `named_grads` (reference parameter name -> tensor shaped like the
+        parameter) and, if given, the gradient of the features."""
+        d = self.device
+        items = list(named_grads)
+        arr = (GwParam * max(1, len(items)))()
+        for i, (k, v) in enumerate(items):
+            rows, cols = (v.shape[0], v.shape[1]) if v.dim() == 2 else (v.numel(), 1)
+            arr[i] = GwParam(k.encode(), _ptr(v, torch.float32, d).value, rows, cols)
+        with torch.cuda.device(d):
+            gf = _ptr(grad_features, torch.float32, d) if grad_features is not None else _vp()
+            _check(self.lib.gw_train_backward(self.handle, _ptr(grad_out, torch.float32, d), gf, arr, len(items), _stream(d)))
 
     def set_output_peers(self, mode: int, deltas=()):
         """Fused loss-boundary gather (gw_plan_set_output_peers): mode 0 off, 1 multicast alias, 2 peer mappings."""

@@ -94,7 +94,12 @@ struct DevBuf {
 
 using namespace gw;
 
+namespace gw {
+struct TrainState;
+}
+
 struct gw_plan {
+  gw::TrainState* train = nullptr;  // training step state (gw_train.inl), created on first use
   gw_dims d;
   int device = 0;
   int n_in_cur = 0;
@@ -1048,6 +1053,10 @@ static int encoder_degree(gw_plan* p, cudaStream_t st) {
   return 0;
 }
 
+}  // namespace gw
+#include "gw_train.inl"
+namespace gw {
+
 enum { NEED_ENC = 1, NEED_PROC = 2, NEED_DEC = 4 };
 static int check_ready(gw_plan* p, int batch, int need) {
   GW_CHECK(p != nullptr, "null plan");
@@ -1191,6 +1200,13 @@ int gw_plan_destroy(gw_plan* p) {
   p->bounds.release(), p->dec_dst.release(), p->seg_carry.release(), p->deg_stats.release(), p->enc_deg.release();
   p->h3_frames.release(), p->h3_lat.release(), p->h3_lng.release(), p->h3_cell_of.release(), p->h3_slot.release(), p->obs_ws.release();
   p->enc_chunk_seg.release(), p->enc_chunk_j0.release(), p->enc_seg_chunk0.release(), p->enc_partial.release();
+  if (p->train) {
+    gw::tfree_all(p->train);
+    p->train->wT.release(), p->train->gbuf.release(), p->train->lat_perm_src.release(), p->train->lat_ptr_src.release();
+    p->train->dec_perm_src.release(), p->train->dec_ptr_src.release(), p->train->iota.release(), p->train->sort_ws.release();
+    delete p->train;
+    p->train = nullptr;
+  }
   if (p->tc_status_host) cudaFreeHost(p->tc_status_host);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1378,6 +1394,31 @@ int gw_forward_strided(gw_plan* p, const float* features, float* out, int32_t ou
   GW_TRY(gw::stage_encoder(p, features, p->xbuf0.p, gw::sl(p, gw::SL_X0), batch, st));
   GW_TRY(gw::stage_processor(p, gw::latent_graph_of(p), p->xbuf0.p, p->xbuf0.p, gw::SL_X0, gw::SL_X0, batch, st));
   return gw::stage_decoder(p, p->xbuf0.p, gw::SL_X0, p->d.residual_dim > 0 ? features : nullptr, p->d.in_dim, out, out_ld, batch, st);
+}
+
+int gw_train_forward(gw_plan* p, const float* features, float* out, int32_t batch, void* stream) {
+  GW_TRY(gw::check_ready(p, batch, gw::NEED_ENC | gw::NEED_PROC | gw::NEED_DEC));
+  GW_CHECK(features && out, "null argument");
+  if (!p->train) p->train = new gw::TrainState();
+  return gw::train_forward(p, p->train, features, out, batch, (cudaStream_t)stream);
+}
+
+int gw_train_backward(gw_plan* p, const float* grad_out, float* grad_features, const gw_param* grads, int32_t n, void* stream) {
+  GW_CHECK(p && grad_out && (n == 0 || grads), "null argument");
+  GW_CHECK(p->train != nullptr, "gw_train_backward needs a preceding gw_train_forward");
+  GW_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  GW_TRY(gw::train_backward(p, p->train, grad_out, grad_features, st));
+  for (int i = 0; i < n; ++i) {  // gradients are handed out under the reference's parameter names, shaped like the parameters
+    GW_CHECK(grads[i].name && grads[i].data, "malformed gw_param entry");
+    auto it = p->params.find(grads[i].name);
+    GW_CHECK(it != p->params.end(), std::string("gw_train_backward: unknown parameter '") + grads[i].name + "'");
+    const size_t cnt = (size_t)it->second.second.first * it->second.second.second;
+    GW_CHECK((size_t)grads[i].rows * grads[i].cols == cnt, std::string("gw_train_backward: shape of '") + grads[i].name + "' differs");
+    GW_CUDA(cudaMemcpyAsync(const_cast<float*>(grads[i].data), p->train->gbuf.p + (it->second.first - p->wbuf.p), cnt * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
 }
 
 int gw_plan_set_output_peers(gw_plan* p, int32_t mode, int32_t n, const int64_t* deltas_bytes) {

@@ -114,4 +114,30 @@ cudaError_t launch_obs_graph(const H3Tables& t, const float* llh, int n, int n_s
   return cudaGetLastError();
 }
 
+// ---- CSR of a graph's edges by SOURCE (backward of the x[src] gathers: a per-source sum of edge gradients) ---------------------
+__global__ void gw_iota_keys_kernel(const int32_t* __restrict__ src, int n, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = (uint32_t)src[i], val[i] = i;
+}
+size_t sort_csr_workspace_bytes(int n) { return obs_graph_workspace_bytes(n); }
+// perm[j] = edge ids ordered by src (ties in edge order), ptr[s] = first position of source s; ws >= sort_csr_workspace_bytes(n)
+cudaError_t launch_sort_csr(const int32_t* src, int n, int n_slots, int32_t* perm, int32_t* ptr, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const size_t nb = (((size_t)n * 4 + 255) / 256) * 256;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  uint32_t* key = reinterpret_cast<uint32_t*>(w);
+  uint32_t* key_sorted = reinterpret_cast<uint32_t*>(w + nb);
+  int32_t* val = reinterpret_cast<int32_t*>(w + 2 * nb);
+  void* sort_ws = w + 3 * nb;
+  size_t sort_bytes = ws_bytes - 3 * nb;
+  gw_iota_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n, key, val);
+  int bits = 1;
+  while ((1 << bits) < n_slots) ++bits;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_ws, sort_bytes, key, key_sorted, val, perm, n, 0, bits, st);
+  if (e != cudaSuccess) return e;
+  gw_csr_from_sorted_kernel<<<(n_slots + 1 + 255) / 256, 256, 0, st>>>(key_sorted, n, n_slots, ptr);
+  count_launch(3);
+  return cudaGetLastError();
+}
+
 }  // namespace gw

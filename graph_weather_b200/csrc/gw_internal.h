@@ -17,6 +17,17 @@ cudaError_t launch_rowop_simt(const GemmOp& op, cudaStream_t stream);
 cudaError_t launch_pad_rows(const float* src, int ld_src, int width, float* dst, int ld_dst, long long rows, float* amax, cudaStream_t stream);
 cudaError_t launch_absmax_flat(const float* p, long long n, float* amax, cudaStream_t stream);
 cudaError_t launch_csr_expand(const int32_t* ptr, int n, int32_t* dst, int* stats, cudaStream_t stream);
+// backward primitives (gw_simt.cu)
+cudaError_t launch_wgrad(const float* dY, int ldy, int N, const RowSrc& a, int K, int rows_per_sample, int batch, float* dW, int ldw, float* db,
+                         cudaStream_t st);
+cudaError_t launch_ln_bwd(const float* dy, int ld_dy, const float* z, int ld_z, int N, const float* gamma, long long R, float* dz, int ld_dz,
+                          float* dgamma, float* dbeta, cudaStream_t st);
+cudaError_t launch_batch_reduce(const float* in, int ld_in, long long rows, int width, int batch, float* out, int ld_out, bool accumulate,
+                                cudaStream_t st);
+cudaError_t launch_gather_rows(const float* in, int ld_in, int src_rows, const int32_t* idx, long long rows, int width, int batch, float* out,
+                               int ld_out, bool accumulate, cudaStream_t st);
+cudaError_t launch_strided_add(const float* src, int ld_src, float* dst, int ld_dst, long long rows, int width, cudaStream_t st);
+cudaError_t launch_transpose(const float* W, int rows, int cols, float* WT, cudaStream_t st);
 int seg_chunk_bound(int n_seg, int n_rows);
 cudaError_t launch_seg_chunks(const int32_t* ptr, int n_seg, int32_t* chunk_seg, int32_t* chunk_j0, int32_t* seg_chunk0, cudaStream_t st);
 cudaError_t launch_segsum_chunked(const float* base, int ld, const int32_t* ptr, const int32_t* perm, int src_rows, int rows, int batch,
@@ -48,6 +59,8 @@ struct H3Tables {
 };
 
 size_t obs_graph_workspace_bytes(int n);
+size_t sort_csr_workspace_bytes(int n);
+cudaError_t launch_sort_csr(const int32_t* src, int n, int n_slots, int32_t* perm, int32_t* ptr, void* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t launch_obs_graph(const H3Tables& t, const float* llh, int n, int n_slots, int32_t* slot, int32_t* perm, int32_t* ptr, float* attr,
                              void* ws, size_t ws_bytes, int32_t* status, cudaStream_t st);
 

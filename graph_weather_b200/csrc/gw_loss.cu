@@ -68,9 +68,46 @@ __global__ void gw_loss_final_kernel(const double* __restrict__ partial, int n, 
 
 constexpr int LOSS_GRID = 148 * 8;
 
+// d(sum) / d pred[b, n, f] * scale = scale * w(n) * 2 (pred - target) * inv_var(f) / F          (losses.py:70-94 differentiated)
+__global__ void __launch_bounds__(256) gw_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                           const float* __restrict__ inv_variance, const float* __restrict__ node_weight,
+                                                           long long rows, int n_nodes, int F, const float* __restrict__ scale_dev, float scale,
+                                                           float* __restrict__ grad) {
+  const float sc = (scale_dev ? __ldg(scale_dev) : 1.f) * scale * 2.f / (float)F;
+  const long long total = rows * F;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / F;
+    const int f = (int)(e - r * F);
+    const float w = __ldg(node_weight + (int)(r % n_nodes));
+    const float iv = inv_variance ? __ldg(inv_variance + f) : 1.f;
+    grad[e] = sc * w * iv * (__ldg(pred + e) - __ldg(target + e));
+  }
+}
+
 }  // namespace gw
 
 extern "C" {
+
+int gw_normalized_mse_loss_grad(const float* pred, const float* target, const float* inv_variance, const float* node_weight, int64_t batch,
+                                int64_t n_nodes, int32_t n_features, const float* scale_dev, float scale, float* grad_pred, void* stream) {
+  if (!pred || !target || !node_weight || !grad_pred) {
+    gw::set_error("gw_normalized_mse_loss_grad: null argument");
+    return 1;
+  }
+  if (batch <= 0 || n_nodes <= 0 || n_features <= 0 || n_nodes > 0x7fffffffLL) {
+    gw::set_error("gw_normalized_mse_loss_grad: bad shape");
+    return 1;
+  }
+  gw::gw_loss_grad_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(pred, target, inv_variance, node_weight, (long long)batch * n_nodes, (int)n_nodes,
+                                                                   n_features, scale_dev, scale, grad_pred);
+  gw::count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    gw::set_error(std::string("loss gradient kernel failed to launch: ") + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
 
 int64_t gw_loss_workspace_bytes(void) { return (int64_t)gw::LOSS_GRID * (int64_t)sizeof(double); }
 

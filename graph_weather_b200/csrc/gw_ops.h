@@ -54,6 +54,8 @@ struct GemmOp {
   RowSrc residual;             // added after LN
   float* out = nullptr;        // out[(b*rows + i)*ldo + n]
   int32_t ldo = 0;
+  float* save_pre = nullptr;   // training: the value entering LayerNorm is also stored here (same ldo) -- LayerNorm's backward needs it
+  RowSrc mask;                 // backward of ReLU: the result is kept where mask(row, n) > 0 and zeroed elsewhere (applied last)
 };
 
 // ---- tensor-core chain (gw_tc3.cu) -------------------------------------------------------------------------------

@@ -11,6 +11,8 @@
 // owns 8 complete rows, so LayerNorm statistics are 5 shuffles.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "gw_ops.h"
 #include "gw_internal.h"
 
@@ -129,6 +131,13 @@ __global__ void __launch_bounds__(NT) gw_rowop_f32_kernel(const GemmOp op) {
       }
       v[j] = x;
     }
+    if (op.save_pre && row_ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int gn = col0 + tx + 32 * j;
+        if (gn < N) op.save_pre[(size_t)gr * op.ldo + gn] = v[j];
+      }
+    }
     if (op.ln_gamma) {  // LayerNorm over N (<= 256, one CTA column block), eps = 1e-5, biased variance (torch)
       float s = 0.f;
 #pragma unroll
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(NT) gw_rowop_f32_kernel(const GemmOp op) {
         if (gn < N) {
           float x = v[j];
           if (op.residual.kind != SRC_NONE) x += fetch_src(op.residual, b, li, gn);
+          if (op.mask.kind != SRC_NONE && !(fetch_src(op.mask, b, li, gn) > 0.f)) x = 0.f;
           op.out[(size_t)gr * op.ldo + gn] = x;
         }
       }
@@ -295,6 +305,234 @@ cudaError_t launch_segsum_chunked(const float* base, int ld, const int32_t* ptr,
                                                                 partial, out, ldo);
   gw_segsum_finish_kernel<<<dim3(rows, batch), 64, 0, st>>>(partial, seg_chunk0, rows, max_chunks, out, ldo);
   count_launch(2);
+  return cudaGetLastError();
+}
+
+// ---- backward primitives (exact fp32; gw_train.inl) -------------------------------------------------------------------------
+// dW[n, k] += sum_r dY[r, n] * A[r, k]   (and db[n] += sum_r dY[r, n]) over R = rows_per_sample * batch rows, A assembled from a row
+// source like the forward kernel does.  Tile: all N <= 256 output rows x 32 k-columns per CTA column (blockIdx.y), the rows are
+// cut into gridDim.x slabs; every CTA accumulates its slab in registers (8 n x 4 k per thread) and adds it to dW with float
+// atomics (summation order across slabs is not fixed: gradients repeat to ~1e-7 relative, not bit for bit).
+constexpr int WG_KT = 32, WG_RT = 16;
+__global__ void __launch_bounds__(256) gw_wgrad_kernel(const float* __restrict__ dY, int ldy, int N, RowSrc a, int K, int rows_per_sample, int batch,
+                                                       float* __restrict__ dW, int ldw, float* __restrict__ db) {
+  __shared__ float Ys[WG_RT][256 + 1];
+  __shared__ float As[WG_RT][WG_KT + 1];
+  const int tid = threadIdx.x, tn = tid & 31, tk = tid >> 5;  // thread: n = tn + 32 i (i < 8), k = 4 tk + j (j < 4)
+  const long long R = (long long)rows_per_sample * batch;
+  const long long per = (R + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(R, r0 + per);
+  const int k0 = blockIdx.y * WG_KT;
+  float acc[8][4];
+  float bacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  for (long long rb = r0; rb < r1; rb += WG_RT) {
+    for (int e = tid; e < WG_RT * 256; e += 256) {
+      const int r = e >> 8, n = e & 255;
+      const long long gr = rb + r;
+      Ys[r][n] = (gr < r1 && n < N) ? __ldg(dY + gr * ldy + n) : 0.f;
+    }
+    for (int e = tid; e < WG_RT * WG_KT; e += 256) {
+      const int r = e / WG_KT, kk = e % WG_KT;
+      const long long gr = rb + r;
+      float v = 0.f;
+      if (gr < r1 && k0 + kk < K) {
+        const int b = (int)(gr / rows_per_sample), i = (int)(gr - (long long)b * rows_per_sample);
+        v = fetch_src(a, b, i, k0 + kk);
+      }
+      As[r][kk] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < WG_RT; ++r) {
+      float y[8], x[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = Ys[r][tn + 32 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = As[r][4 * tk + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bacc[i] += y[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(y[i], x[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = tn + 32 * i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * tk + j;
+      if (k < K) atomicAdd(dW + (size_t)n * ldw + k, acc[i][j]);
+    }
+    if (db && blockIdx.y == 0 && tk == 0) atomicAdd(db + n, bacc[i]);
+  }
+}
+cudaError_t launch_wgrad(const float* dY, int ldy, int N, const RowSrc& a, int K, int rows_per_sample, int batch, float* dW, int ldw, float* db,
+                         cudaStream_t st) {
+  const long long R = (long long)rows_per_sample * batch;
+  if (R <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  if (N > 256) return cudaErrorInvalidValue;
+  const int slabs = (int)std::min<long long>(296, (R + 255) / 256);
+  gw_wgrad_kernel<<<dim3(slabs, (K + WG_KT - 1) / WG_KT), 256, 0, st>>>(dY, ldy, N, a, K, rows_per_sample, batch, dW, ldw, db);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// LayerNorm backward over rows of N <= 256 columns (one warp per row, rows grid-strided):
+//   zh = (z - mean) * rstd;  g = dy * gamma;  dz = rstd * (g - mean(g) - zh * mean(g * zh));  dgamma += dy * zh;  dbeta += dy
+__global__ void __launch_bounds__(256) gw_ln_bwd_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ z, int ld_z, int N,
+                                                        const float* __restrict__ gamma, long long R, float* __restrict__ dz, int ld_dz,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sg[8][256], sb[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+  for (long long r = (long long)blockIdx.x * 8 + w; r < R; r += (long long)gridDim.x * 8) {
+    float zv[8], gv[8], dv[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      zv[j] = c < N ? __ldg(z + r * ld_z + c) : 0.f;
+      dv[j] = c < N ? __ldg(dy + r * ld_dy + c) : 0.f;
+      s += zv[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = (lane + 32 * j < N) ? zv[j] - mean : 0.f;
+      q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q / (float)N + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      const bool ok = c < N;
+      zv[j] = ok ? (zv[j] - mean) * rstd : 0.f;
+      gv[j] = ok ? dv[j] * __ldg(gamma + c) : 0.f;
+      m1 += gv[j], m2 += gv[j] * zv[j];
+      ag[j] += dv[j] * zv[j], ab[j] += dv[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m1 += __shfl_xor_sync(0xffffffffu, m1, o), m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    m1 /= (float)N, m2 /= (float)N;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      if (c < N) dz[r * ld_dz + c] = rstd * (gv[j] - m1 - zv[j] * m2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sg[w][lane + 32 * j] = ag[j], sb[w][lane + 32 * j] = ab[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c < N) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g += sg[k][c], b += sb[k][c];
+    atomicAdd(dgamma + c, g), atomicAdd(dbeta + c, b);
+  }
+}
+cudaError_t launch_ln_bwd(const float* dy, int ld_dy, const float* z, int ld_z, int N, const float* gamma, long long R, float* dz, int ld_dz,
+                          float* dgamma, float* dbeta, cudaStream_t st) {
+  if (R <= 0) return cudaSuccess;
+  if (N > 256) return cudaErrorInvalidValue;
+  gw_ln_bwd_kernel<<<(unsigned)std::min<long long>(148 * 8, (R + 7) / 8), 256, 0, st>>>(dy, ld_dy, z, ld_z, N, gamma, R, dz, ld_dz, dgamma, dbeta);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// out[i, c] (+)= sum_b in[(b * rows + i), c]     (gradient of a tensor that the forward broadcast over the batch)
+__global__ void gw_batch_reduce_kernel(const float* __restrict__ in, int ld_in, long long rows, int width, int batch, float* __restrict__ out, int ld_out,
+                                       int accumulate) {
+  const long long total = rows * width;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / width;
+    const int c = (int)(e - i * width);
+    float s = accumulate ? out[i * ld_out + c] : 0.f;
+    for (int b = 0; b < batch; ++b) s += __ldg(in + ((long long)b * rows + i) * ld_in + c);
+    out[i * ld_out + c] = s;
+  }
+}
+cudaError_t launch_batch_reduce(const float* in, int ld_in, long long rows, int width, int batch, float* out, int ld_out, bool accumulate,
+                                cudaStream_t st) {
+  if (rows <= 0 || width <= 0) return cudaSuccess;
+  gw_batch_reduce_kernel<<<148 * 4, 256, 0, st>>>(in, ld_in, rows, width, batch, out, ld_out, accumulate ? 1 : 0);
+  count_launch();
+  return cudaGetLastError();
+}
+// out[(b * rows + j), c] (+)= in[(b * src_rows + idx[j]), c]   (gradient of a per-target sum: every row receives its target's gradient)
+__global__ void gw_gather_rows_kernel(const float* __restrict__ in, int ld_in, int src_rows, const int32_t* __restrict__ idx, long long rows, int width,
+                                      int batch, float* __restrict__ out, int ld_out, int accumulate) {
+  const long long total = rows * batch * (width >> 2);
+  const int q = width >> 2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long rj = e / q;
+    const int c = (int)(e - rj * q) * 4;
+    const long long b = rj / rows, j = rj - b * rows;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + (b * src_rows + __ldg(idx + j)) * ld_in + c));
+    float4* o = reinterpret_cast<float4*>(out + rj * ld_out + c);
+    if (accumulate) {
+      float4 t = *o;
+      t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+      *o = t;
+    } else {
+      *o = v;
+    }
+  }
+}
+cudaError_t launch_gather_rows(const float* in, int ld_in, int src_rows, const int32_t* idx, long long rows, int width, int batch, float* out,
+                               int ld_out, bool accumulate, cudaStream_t st) {
+  if (rows <= 0 || batch <= 0) return cudaSuccess;
+  if ((width & 3) || (ld_in & 3) || (ld_out & 3)) return cudaErrorInvalidValue;
+  gw_gather_rows_kernel<<<148 * 8, 256, 0, st>>>(in, ld_in, src_rows, idx, rows, width, batch, out, ld_out, accumulate ? 1 : 0);
+  count_launch();
+  return cudaGetLastError();
+}
+// dst[r, c] += src[r, c] for c < width (rows of different strides)
+__global__ void gw_strided_add_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst, long long rows, int width) {
+  const long long total = rows * width;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / width;
+    const int c = (int)(e - r * width);
+    dst[r * ld_dst + c] += __ldg(src + r * ld_src + c);
+  }
+}
+cudaError_t launch_strided_add(const float* src, int ld_src, float* dst, int ld_dst, long long rows, int width, cudaStream_t st) {
+  if (rows <= 0 || width <= 0) return cudaSuccess;
+  gw_strided_add_kernel<<<148 * 4, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, width);
+  count_launch();
+  return cudaGetLastError();
+}
+// WT[k, n] = W[n, k]   (data gradients multiply by the untransposed weight: the row-op kernel wants it as [out-of-op, in-of-op])
+__global__ void gw_transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ WT) {
+  __shared__ float t[32][33];
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (x < cols && y0 + j < rows) t[j][threadIdx.x] = W[(size_t)(y0 + j) * cols + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (xo < rows && yo0 + j < cols) WT[(size_t)(yo0 + j) * rows + xo] = t[threadIdx.x][j];
+}
+cudaError_t launch_transpose(const float* W, int rows, int cols, float* WT, cudaStream_t st) {
+  gw_transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, st>>>(W, rows, cols, WT);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -119,6 +119,15 @@ int gw_forward(gw_plan* plan, const float* features, float* out, int32_t batch, 
  * no concatenation pass exists between steps. */
 int gw_forward_strided(gw_plan* plan, const float* features, float* out, int32_t out_ld, int32_t batch, void* stream);
 
+/* Training step ("then backward"; every caller of the reference trains, train/run.py:508-543).
+ * gw_train_forward is gw_forward on the exact-fp32 plan (precision GW_PREC_FP32_SIMT) that keeps the activations the backward
+ * needs; gw_train_backward consumes them: grad_out [batch, n_out, out_dim] -> gradients of every parameter, copied into the
+ * caller's tensors named like the parameters (`grads`: reference state_dict keys, device pointers, parameter shapes), and, if
+ * grad_features is not NULL, the gradient of the input features [batch, n_in, in_dim].  One backward per forward.  LayerNorm MLPs,
+ * dims <= 256.  Weight gradients are accumulated with float atomics (repeatable to ~1e-7 relative, not bit for bit). */
+int gw_train_forward(gw_plan* plan, const float* features, float* out, int32_t batch, void* stream);
+int gw_train_backward(gw_plan* plan, const float* grad_out, float* grad_features, const gw_param* grads, int32_t n, void* stream);
+
 /* Multi-GPU loss boundary fused into the forecast's last chain (the one gather of the outputs).  After this call
  * every gw_forward / gw_forward_strided / gw_decoder_forward stores its `out` rows, as the tiles leave the tensor cores, into
  * the gather buffers of every GPU of the job as well:
@@ -204,6 +213,11 @@ int gw_normalized_mse_loss_sum(const float* pred, const float* target, const flo
 int64_t gw_constraint_workspace_bytes(int64_t batch, int32_t channels);
 int gw_constraint_apply(int32_t type, const float* hr, const float* lr, int32_t lr_ld, int32_t lr_channels, const int32_t* src,
                         float* out, int64_t batch, int64_t n_nodes, int32_t channels, float exp_factor, void* workspace, void* stream);
+
+/* Backward of the loss sum: grad_pred[b, n, f] = (*scale_dev) * scale * node_weight[n] * 2 (pred - target) * inv_variance[f] / n_features.
+ * scale_dev (device float, may be NULL = 1) carries the upstream gradient; scale is a host factor (1 / global row count). */
+int gw_normalized_mse_loss_grad(const float* pred, const float* target, const float* inv_variance, const float* node_weight, int64_t batch,
+                                int64_t n_nodes, int32_t n_features, const float* scale_dev, float scale, float* grad_pred, void* stream);
 
 /* Counters for bench.py: kernels launched by this library on the calling thread since the last reset. */
 int64_t gw_launch_count(void);
