@@ -501,4 +501,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    with torch.no_grad():  # an inference benchmark (forward steps/s): autograd off, like any evaluation loop
+        main()

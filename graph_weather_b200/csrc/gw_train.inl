@@ -141,7 +141,6 @@ static int train_prepare(gw_plan* p, TrainState* T, int batch, cudaStream_t st) 
   GW_CHECK(p->w_enc && p->w_proc && p->w_dec && p->have_enc && p->have_lat && p->have_dec, "training needs the full forecaster (graphs + weights)");
   GW_CHECK(d.node_dim <= 256 && d.edge_dim <= 256 && d.hidden_node <= 256 && d.hidden_edge <= 256 && d.hidden_dec <= 256 && d.out_dim <= 256,
            "training kernels cover dims <= 256");
-  GW_CHECK(d.node_dim == d.edge_dim || true, "");
   T->st = st;
   if (T->wT.n != p->wbuf.n) GW_TRY(T->wT.alloc(p->wbuf.n));
   if (T->gbuf.n != p->wbuf.n) GW_TRY(T->gbuf.alloc(p->wbuf.n));

@@ -27,10 +27,12 @@ def _as_latlon_array(lat_lons) -> np.ndarray:
 
 
 def validate_lat_lons(lat_lons) -> None:
-    """Same checks and ValueError as graph_weather/utils.py:6-12."""
-    for lat, lon in lat_lons:
-        if not (-90 <= lat <= 90 and -180 <= lon <= 360):
-            raise ValueError(f"Invalid lat/lon: ({lat}, {lon})")
+    """Same checks and messages as graph_weather/utils.py:6-12: non-empty, every latitude inside [-90, 90]."""
+    if len(lat_lons) == 0:
+        raise ValueError("lat_lons must not be empty.")
+    for index, (lat, _lon) in enumerate(lat_lons):
+        if not (-90.0 <= lat <= 90.0):
+            raise ValueError(f"Coordinate {index}: latitude {lat} is outside [-90, 90].")
 
 
 def _sincos_attr(lat1_deg, lng1_deg, lat2_deg, lng2_deg) -> np.ndarray:

@@ -27,6 +27,34 @@ def node_weights(lat_lons, num_nodes: int) -> np.ndarray:
     return np.repeat(w, num_lon)
 
 
+class _LossFn(torch.autograd.Function):
+    """value = sum_all_ranks(local sums) / rows;  d value / d pred = w(n) 2 (pred - target) inv_var / (F rows)  (one kernel)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, crit, group, total_batch):
+        s = crit.local_sum(pred, target)
+        nodes = int(np.prod(pred.shape[1:-1]))
+        rows = pred.shape[0] * nodes
+        if group is not None or total_batch is not None:
+            import torch.distributed as dist
+
+            if total_batch is None:
+                cnt = torch.tensor([float(pred.shape[0])], dtype=torch.float64, device=s.device)
+                dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+                total_batch = int(round(float(cnt.item())))
+            s = s.clone()
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+            rows = int(total_batch) * nodes
+        ctx.crit, ctx.rows = crit, rows
+        ctx.save_for_backward(pred.detach(), target.detach())
+        return (s / rows).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_value):
+        pred, target = ctx.saved_tensors
+        return ctx.crit.grad_pred(pred, target, grad_value, 1.0 / ctx.rows), None, None, None, None
+
+
 class NormalizedMSELoss(torch.nn.Module):
     """Variance-normalised, cos(lat)-weighted MSE (losses.py:9-94): same constructor, same `forward(pred, target)` value."""
 
@@ -78,9 +106,32 @@ class NormalizedMSELoss(torch.nn.Module):
                 ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(st)))  # fmt: skip
         return s
 
+    def grad_pred(self, pred: torch.Tensor, target: torch.Tensor, upstream: torch.Tensor, scale: float) -> torch.Tensor:
+        """upstream * scale * d(local sum)/d pred as one kernel (gw_normalized_mse_loss_grad); `upstream` is a 0-d device tensor."""
+        lib = _capi.load()
+        B, F = pred.shape[0], pred.shape[-1]
+        num_nodes = int(np.prod(pred.shape[1:-1]))
+        p = pred.detach().to(torch.float32).contiguous()
+        t = target.detach().to(torch.float32).contiguous()
+        inv, w, _, _ = self._device_state(pred.device, num_nodes, F)
+        up = upstream.detach().to(device=pred.device, dtype=torch.float32).reshape(1).contiguous()
+        g = torch.empty_like(p)
+        if B == 0:
+            return g
+        with torch.cuda.device(pred.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _capi._check(lib.gw_normalized_mse_loss_grad(
+                ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(inv.data_ptr()) if self.normalize else None,
+                ctypes.c_void_p(w.data_ptr()), B, num_nodes, F, ctypes.c_void_p(up.data_ptr()), float(scale), ctypes.c_void_p(g.data_ptr()),
+                ctypes.c_void_p(st)))  # fmt: skip
+        return g.reshape(pred.shape)
+
     def forward(self, pred: torch.Tensor, target: torch.Tensor, group=None, total_batch: int | None = None):
         """losses.py:46-94.  With `group` (torch.distributed), `pred` / `target` are this rank's batch shard and the result is
-        the loss over the whole batch of `total_batch` samples: the ranks exchange one scalar."""
+        the loss over the whole batch of `total_batch` samples: the ranks exchange one scalar.  Differentiable with respect
+        to `pred` (training: `loss.backward()` runs gw_normalized_mse_loss_grad, then the model's CUDA backward)."""
+        if torch.is_grad_enabled() and pred.requires_grad:
+            return _LossFn.apply(pred, target, self, group, total_batch)
         s = self.local_sum(pred, target)
         nodes = int(np.prod(pred.shape[1:-1]))
         rows = pred.shape[0] * nodes

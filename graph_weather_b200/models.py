@@ -206,6 +206,44 @@ def _maybe_check(plan):
         plan.status()
 
 
+class _ForecastTrainFn(torch.autograd.Function):
+    """autograd node of one training forward of GraphWeatherForecaster: forward = gw_train_forward (exact fp32, activations
+    kept in the plan), backward = gw_train_backward (gradients of every parameter under its reference name, and of the
+    features when they require grad).  One backward per forward: the plan holds a single tape."""
+
+    @staticmethod
+    def forward(ctx, model, features, *params):
+        B = features.shape[0]
+        eng = model._training_engine()
+        plan = eng.ensure(features.device, B, model._named())
+        f = features.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, model.decoder.num_latlons, model.output_dim), dtype=torch.float32, device=f.device)
+        plan.train_forward(f, out)
+        eng.tape_id = getattr(eng, "tape_id", 0) + 1
+        ctx.model, ctx.plan, ctx.eng, ctx.tape_id = model, plan, eng, eng.tape_id
+        ctx.feat_shape, ctx.feat_grad = tuple(f.shape), bool(features.requires_grad)
+        ctx.names = [k for k, _ in model.named_parameters()]
+        ctx.pshapes = [tuple(q.shape) for q in params]
+        ctx.pgrad = [bool(q.requires_grad) for q in params]
+        ctx.keep = f  # the tape reads the features again in the backward (weight gradient of the first Linear)
+        _maybe_check(plan)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.eng.tape_id != ctx.tape_id or ctx.eng.plan is not ctx.plan:
+            raise RuntimeError("graph_weather_b200: backward of a forward whose activations were replaced by a later training "
+                               "forward (one backward per forward: the plan keeps a single tape)")
+        dev = grad_out.device
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gfeat = torch.empty(ctx.feat_shape, dtype=torch.float32, device=dev) if ctx.feat_grad else None
+        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.pshapes]
+        ctx.plan.train_backward(g, gfeat, list(zip(ctx.names, grads)))
+        ctx.eng.tape_id += 1  # the tape is consumed
+        _maybe_check(ctx.plan)
+        return (None, gfeat) + tuple(gr if need else None for gr, need in zip(grads, ctx.pgrad))
+
+
 def _prefixed(prefix, module):
     return [(f"{prefix}.{k}", v) for k, v in module.state_dict(keep_vars=True).items() if torch.is_tensor(v)]
 
@@ -621,8 +659,27 @@ class GraphWeatherForecaster(nn.Module, PyTorchModelHubMixin):
         cell, _ = self._grid_mapping.tensors(out.device)
         return self.constraint.apply_rows(out, f, cell.to(torch.int32).contiguous(), self.feature_dim)
 
+    def _training_engine(self):
+        """The exact-fp32 plan the training step runs on (created on first use; the inference engine stays as it is)."""
+        if getattr(self, "_train_engine", None) is None:
+            eng = _Engine(self._engine.dims, "fp32_simt")
+            eng.graph_uploaders += [self.encoder._upload_graphs, self.decoder._upload_graphs]
+            self.__dict__["_train_engine"] = eng
+        return self._train_engine
+
+    def _wants_grad(self, features):
+        return torch.is_grad_enabled() and self.training and (features.requires_grad or any(q.requires_grad for q in self.parameters()))
+
     def forward(self, features: torch.Tensor, t: int = 0) -> torch.Tensor:
         self._check_features(features)
+        if self._wants_grad(features):
+            # train mode with autograd on, like every training caller of the reference (train/run.py:508-543): the forward keeps
+            # its activations and `loss.backward()` runs the CUDA backward.  Inference (`model.eval()` or `torch.no_grad()`) takes
+            # the tensor-core path below.
+            if self.constraint_type != "none":
+                raise NotImplementedError("training with a constraint layer is not built (inference only)")
+            params = [q for _, q in self.named_parameters()]
+            return _ForecastTrainFn.apply(self, features, *params)
         B = features.shape[0]
         plan = self._engine.ensure(features.device, B, self._named())
         f = features.detach().to(torch.float32).contiguous()

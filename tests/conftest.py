@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "training: the test differentiates through the model (autograd stays enabled)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -29,3 +30,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _inference_by_default(request):
+    """Forward-parity tests run like an evaluation loop (autograd off: the tensor-core path); tests of the training step
+    mark themselves with `@pytest.mark.training` and get autograd back."""
+    import torch
+
+    if "training" in request.keywords:
+        yield
+        return
+    with torch.no_grad():
+        yield

@@ -1,0 +1,101 @@
+"""-m gpu: the training step (backward).  `model(features)` in train mode with autograd on, the CUDA
+NormalizedMSELoss and `loss.backward()` against torch.autograd on the CPU oracle (the reference's own ops, oracle/restate.py):
+the loss value, the gradient of the features and the gradient of every one of the 215 parameters."""
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as ge
+
+pytestmark = [pytest.mark.gpu, pytest.mark.training]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    ge.build()
+
+
+def _grid(step):
+    return [(float(lat), float(lon)) for lat in range(-90, 90, step) for lon in range(0, 360, step)]
+
+
+def _oracle_step(sd, ll, x, target, var):
+    from oracle import restate
+
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xg = x.clone().requires_grad_(True)
+    g = restate.build_forecaster_graphs(ll)
+    ex, ei, ea = restate.encoder_forward(sd_g, g, xg)
+    px = restate.processor_forward(sd_g, ex, ei, ea, 9)
+    out = restate.assimilator_decoder_forward(sd_g, g, px, x.shape[0]) + xg[..., :78]
+    loss = restate.normalized_mse_loss(out, target, var, ll, True)
+    loss.backward()
+    return out.detach(), float(loss), xg.grad, {k: v.grad for k, v in sd_g.items()}
+
+
+def test_training_step_matches_autograd_on_the_oracle():
+    from graph_weather_b200 import GraphWeatherForecaster, NormalizedMSELoss
+    from oracle import weights
+
+    ll = _grid(10)
+    sd = weights.make_state_dict(weights.forecaster_shapes(), 21)
+    x = weights.make_features(2, len(ll), 102, 21)
+    rng = np.random.Generator(np.random.PCG64(21))
+    target = torch.from_numpy(rng.standard_normal((2, len(ll), 78)).astype(np.float32))
+    var = rng.uniform(0.5, 2.0, 78).astype(np.float32).tolist()
+    out_ref, loss_ref, gx_ref, g_ref = _oracle_step(sd, ll, x, target, var)
+
+    model = GraphWeatherForecaster(ll).cuda().train()
+    model.load_state_dict(sd)
+    crit = NormalizedMSELoss(var, ll, normalize=True)
+    xc = x.cuda().requires_grad_(True)
+    out = model(xc)
+    assert out.requires_grad and float((out.detach().cpu() - out_ref).abs().max()) < 1e-4
+    loss = crit(out, target.cuda())
+    assert abs(float(loss) - loss_ref) <= 1e-5 * abs(loss_ref)
+    loss.backward()
+    model._train_engine.plan.status()
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12)
+
+    worst = ("", 0.0)
+    e = rel(xc.grad.cpu(), gx_ref)
+    print(f"d loss / d features: rel err {e:.2e} (|ref| max {float(gx_ref.abs().max()):.2e})")
+    assert e < 1e-4
+    names = [k for k, _ in model.named_parameters()]
+    assert set(names) == set(g_ref.keys()) and len(names) == 215
+    for k, q in model.named_parameters():
+        assert q.grad is not None and q.grad.shape == q.shape, k
+        e = rel(q.grad.cpu(), g_ref[k])
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 1e-4, (k, e)
+    print(f"worst parameter gradient: {worst[0]} rel err {worst[1]:.2e}")
+    # a second step after an optimiser update: weights are re-uploaded, the tape is fresh
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    opt.step()
+    opt.zero_grad()
+    loss2 = crit(model(x.cuda()), target.cuda())
+    loss2.backward()
+    assert float(loss2) < float(loss)  # one SGD step on a fixed batch lowers the loss
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in model.parameters())
+    # inference is unchanged by all this: eval + no_grad is the tensor-core path
+    model.eval()
+    with torch.no_grad():
+        y = model(x.cuda())
+    assert not y.requires_grad
+    assert model._engine.resolved_precision in ("fp32", "fp32_simt")
+
+
+def test_one_backward_per_forward():
+    from graph_weather_b200 import GraphWeatherForecaster
+
+    ll = _grid(30)
+    model = GraphWeatherForecaster(ll, num_blocks=2).cuda().train()
+    x = torch.randn(1, len(ll), 102, device="cuda")
+    a = model(x)
+    b = model(x)  # replaces the tape of `a`
+    b.sum().backward()
+    with pytest.raises(RuntimeError, match="one backward per forward"):
+        a.sum().backward()
