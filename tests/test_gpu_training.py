@@ -19,18 +19,20 @@ def _grid(step):
     return [(float(lat), float(lon)) for lat in range(-90, 90, step) for lon in range(0, 360, step)]
 
 
-def _oracle_step(sd, ll, x, target, var):
+def _oracle_step(sd, ll, x, target, var, dtype=torch.float32):
+    """One training step of the reference arithmetic on the CPU under torch.autograd, in fp32 (what the reference runs) or
+    fp64 (ground truth for the tolerance)."""
     from oracle import restate
 
-    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    xg = x.clone().requires_grad_(True)
-    g = restate.build_forecaster_graphs(ll)
+    sd_g = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    xg = x.to(dtype).clone().requires_grad_(True)
+    g = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in restate.build_forecaster_graphs(ll).items()}
     ex, ei, ea = restate.encoder_forward(sd_g, g, xg)
     px = restate.processor_forward(sd_g, ex, ei, ea, 9)
     out = restate.assimilator_decoder_forward(sd_g, g, px, x.shape[0]) + xg[..., :78]
-    loss = restate.normalized_mse_loss(out, target, var, ll, True)
+    loss = restate.normalized_mse_loss(out, target.to(dtype), var, ll, True)
     loss.backward()
-    return out.detach(), float(loss), xg.grad, {k: v.grad for k, v in sd_g.items()}
+    return out.detach(), float(loss.detach()), xg.grad, {k: v.grad for k, v in sd_g.items()}
 
 
 def test_training_step_matches_autograd_on_the_oracle():
@@ -56,22 +58,31 @@ def test_training_step_matches_autograd_on_the_oracle():
     loss.backward()
     model._train_engine.plan.status()
 
-    def rel(a, b):
-        return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12)
+    # Tolerance.  ReLU masks and LayerNorm statistics sit downstream of ~60 fp32 GEMM layers, so two fp32 implementations of the
+    # same step differ by far more than a summation-order ulp (a unit within 1e-6 of zero flips its mask).  The yardstick is
+    # therefore the fp64 ground truth: this implementation must be as close to it as the reference's own fp32 arithmetic is
+    # (within a factor, plus a floor for gradients that are numerically zero).
+    _, loss64, gx64, g64 = _oracle_step(sd, ll, x, target, var, torch.float64)
 
-    worst = ("", 0.0)
-    e = rel(xc.grad.cpu(), gx_ref)
-    print(f"d loss / d features: rel err {e:.2e} (|ref| max {float(gx_ref.abs().max()):.2e})")
-    assert e < 1e-4
+    def rel(a, b):
+        return float((a.double() - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+
+    e_ours, e_ref = rel(xc.grad.cpu(), gx64), rel(gx_ref, gx64)
+    print(f"d loss / d features: rel err vs fp64 {e_ours:.2e} (the fp32 oracle: {e_ref:.2e})")
+    assert e_ours < 10 * e_ref + 2e-5
     names = [k for k, _ in model.named_parameters()]
     assert set(names) == set(g_ref.keys()) and len(names) == 215
+    errs = []
     for k, q in model.named_parameters():
         assert q.grad is not None and q.grad.shape == q.shape, k
-        e = rel(q.grad.cpu(), g_ref[k])
-        if e > worst[1]:
-            worst = (k, e)
-        assert e < 1e-4, (k, e)
-    print(f"worst parameter gradient: {worst[0]} rel err {worst[1]:.2e}")
+        errs.append((rel(q.grad.cpu(), g64[k]), rel(g_ref[k], g64[k]), k, float(g64[k].abs().max())))
+    errs.sort(reverse=True)
+    for eo, er, k, m in errs[:8]:
+        print(f"  {k}: rel err vs fp64 {eo:.2e} (fp32 oracle {er:.2e}; |grad| max {m:.2e})")
+    print(f"median rel err vs fp64: ours {sorted(e[0] for e in errs)[len(errs) // 2]:.2e}, fp32 oracle {sorted(e[1] for e in errs)[len(errs) // 2]:.2e}")
+    for eo, er, k, m in errs:
+        assert eo < 10 * er + 2e-5, (k, eo, er)
+    assert sorted(e[0] for e in errs)[len(errs) // 2] < 3 * sorted(e[1] for e in errs)[len(errs) // 2] + 1e-5
     # a second step after an optimiser update: weights are re-uploaded, the tape is fresh
     opt = torch.optim.SGD(model.parameters(), lr=1e-2)
     opt.step()
