@@ -781,12 +781,12 @@ static int stage_processor(gw_plan* p, const ProcGraph& g, const float* x_in, fl
         }
         ch.n_layers = 3;
         GW_TRY(run_chain(p, ch, st));
-        if (fuse) {
-          TimedLaunch t(p, st);
-          GW_CUDA(launch_seg_carry(p->seg_carry.p, g.dst, El, H, nb, p->agg_mesh.p, De, st));
-        }
       }
       p->cur_tag = TAG_PROC_NODE;
+      if (fuse) {  // (timed with its consumer, like round 1's segment-sum launch: it completes the node chain's aggregate input)
+        TimedLaunch t(p, st);
+        GW_CUDA(launch_seg_carry(p->seg_carry.p, g.dst, El, H, nb, p->agg_mesh.p, De, st));
+      }
       {  // x' = LN(MLP([x ; sum_in e'])) + x
         TcChain ch;
         ch.rows_per_sample = H, ch.batch = nb;
@@ -928,12 +928,12 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
         }
         ch.n_layers = 2;
         GW_TRY(run_chain(p, ch, st));
-        if (fuse) {
-          TimedLaunch t(p, st);
-          GW_CUDA(launch_seg_carry(p->seg_carry.p, p->dec_dst.p, Ed, No, cb, p->agg_grid.p, De, st));
-        }
       }
       p->cur_tag = TAG_DEC_NODE;
+      if (fuse) {
+        TimedLaunch t(p, st);
+        GW_CUDA(launch_seg_carry(p->seg_carry.p, p->dec_dst.p, Ed, No, cb, p->agg_grid.p, De, st));
+      }
       {  // lat/lon node update (x == 0, so only the aggregate half of W1 and no residual)
         TcChain ch;
         ch.rows_per_sample = No, ch.batch = cb;

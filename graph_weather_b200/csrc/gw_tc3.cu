@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           ldfrag4(pb, 256 * (c - NC0), buf[c % DEPTH]);
         }
       };
+      tr.ev(480);
       static_for<0, (NC < DEPTH ? NC : DEPTH)>([&](auto cc) { fetch(cc); });
       if (l0_add0) {
 #pragma unroll
@@ -633,6 +634,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         constexpr int c = decltype(cc)::value;
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
         if (n > 0) mbar_wait(bar_empty_a + 8 * slot, (n - 1) & 1, ch.status);  // the MMAs that read this slot last have completed
+        tr.ev(490 + c);
         float(&cur)[16] = buf[c % DEPTH];
         if constexpr (GBR) {
 #pragma unroll
@@ -742,6 +744,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               s2[k] = fmaf(d, d, s2[k]);
             }
           });
+          tr.ev(2001);
           if constexpr (has0) {
             if (ld_on) ldfrag4(p0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
           }
@@ -768,6 +771,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+          tr.ev(2002);
           constexpr float nw = 16.0f * NP;  // values per warp partial
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -784,6 +788,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             rs[k] = rstd, sh[k] = -mu * rstd;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
+          tr.ev(2003);
         } else if constexpr (has0) {
           if (ld_on) ldfrag4(p0, 0, pf0);
         }
@@ -832,6 +837,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       }
       // The accumulator chunk s+1 is fetched from TMEM while chunk s is processed.
       float vb[2][16] = {};
+      if constexpr (has_ln) tr.ev(2004);
       if (!ABL3(ABL_TMEM)) {
         tmem_ld_16x256b_x2(taddr, vb[0]);
         tmem_ld_16x256b_x2(taddr + (16u << 16), vb[0] + 8);
@@ -840,6 +846,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         constexpr int s = decltype(sc_)::value;
         float(&v)[16] = vb[s & 1];
         tmem_wait_ld_into(v);
+        if constexpr (has_ln) tr.ev(2010 + s);
         if constexpr (s + 1 < NP) {
           if (!ABL3(ABL_TMEM)) {
             tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vb[(s + 1) & 1]);
@@ -883,6 +890,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             for (int i = 0; i < 16; ++i) v[i] += pf0[i];
           }
         }
+        if constexpr (has_ln) tr.ev(2020 + s);
         if constexpr (s + 1 < NP) {  // next chunk's global operands: in flight while this chunk is stored / converted
           if constexpr (has0) {
             if (ld_on) ldfrag4(p0, 256 * (s + 1), pf0);
@@ -902,6 +910,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             }
           }
         }
+        if constexpr (has_ln) tr.ev(2030 + s);
         if constexpr (has_seg) {
           // running sums over my four consecutive rows, restarted at every boundary; T = the piece ending with my row 3,
           // H = the piece before my first inner boundary (all four rows if there is none): what earlier threads add to theirs

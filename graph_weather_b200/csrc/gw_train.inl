@@ -148,6 +148,14 @@ static int train_prepare(gw_plan* p, TrainState* T, int batch, cudaStream_t st) 
     const int64_t r = kv.second.second.first, c = kv.second.second.second;
     if (c > 1) GW_CUDA(launch_transpose(kv.second.first, (int)r, (int)c, T->wT.p + (kv.second.first - p->wbuf.p), st));
   }
+  if (!T->graphs_ready) {  // keep the stream-ordered pool's memory between steps (the default returns it to the driver at every sync)
+    cudaMemPool_t pool = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (!T->graphs_ready) {  // edges grouped by SOURCE (the x[src] gathers become per-source sums going backward)
     const int El = d.n_lat_edges, Ed = d.n_dec_edges, H = d.n_mesh;
     const size_t ws = std::max(sort_csr_workspace_bytes(El), sort_csr_workspace_bytes(Ed));

@@ -23,7 +23,7 @@ def build_abl(extra=()):
     objs = []
     for s in ge.SOURCES:
         o = os.path.join(out, s[:-3] + ".o")
-        subprocess.run([ge.NVCC, *ge.FLAGS, "-DGW_ABLATE", *extra, "-c", os.path.join(ge.CSRC, s), "-o", o], check=True)
+        subprocess.run([ge.NVCC, *ge.FLAGS, *ge.EXTRA_FLAGS.get(s, []), "-DGW_ABLATE", *extra, "-c", os.path.join(ge.CSRC, s), "-o", o], check=True)
         objs.append(o)
     subprocess.run([ge.NVCC, "-shared", "-o", os.path.join(out, "libgwb200.so"), *objs, "-lcudart"], check=True)
     print("built", out)

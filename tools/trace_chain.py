@@ -15,7 +15,8 @@ ge.build()
 from graph_weather_b200 import GraphWeatherForecaster
 ll = [(float(x), float(y)) for x in range(-90, 90) for y in range(0, 360)]
 torch.manual_seed(0)
-m = GraphWeatherForecaster(ll, precision="fp32").cuda()
+torch.set_grad_enabled(False)
+m = GraphWeatherForecaster(ll, precision="fp32").cuda().eval()
 x = torch.randn(a.batch, len(ll), 102, device="cuda")
 for _ in range(2): m(x)
 torch.cuda.synchronize()
@@ -27,5 +28,5 @@ roles = ["producer", "mma", "-", "-", "-", "worker_q0_h0", "worker_q0_h1", "-"]
 t0 = min(int(t[r, 0, 0]) for r in range(8) if t[r, 0, 0] > 0)
 for r in range(8):
     ev = [(int(c) - t0, int(k)) for c, k in t[r] if c > 0]
-    print(roles[r], len(ev), "events; first 70:")
-    print("  " + " ".join(f"{k}@{c}" for c, k in ev[:70]))
+    print(roles[r], len(ev), "events; first 260:")
+    print("  " + " ".join(f"{k}@{c}" for c, k in ev[:260]))
