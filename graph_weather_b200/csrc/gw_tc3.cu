@@ -91,8 +91,8 @@ constexpr int NUM_BARS = 2 * A_SLOTS + 2 * B_STAGES + 4;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_PAR = OFF_TMEM + 16;                // float bias[PAR_LAYERS][256]
 constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;  // float gamma_beta[2][2][256]
-constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_x[WSPLIT][128], ln_y[WSPLIT][128]: row statistics exchange
-constexpr int OFF_PRE = OFF_LN + 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather rows of the coming tile
+constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_xy[2][2][WSPLIT][128]: row statistics exchange (mean, M2), two generations
+constexpr int OFF_PRE = OFF_LN + 2 * 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather rows of the coming tile
 constexpr int OFF_SCL = OFF_PRE + 8 * NUM_WORKERS * 4;  // float scl[2 * PAR_LAYERS + 4]: per layer {accumulator scale, operand scale of the result}, then the stage-0 operand scale
 constexpr int SMEM_BYTES = OFF_SCL + (2 * PAR_LAYERS + 4) * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -242,6 +242,17 @@ __device__ __forceinline__ void row_ptrs(const RowSrc& s, int b, int i0, const i
     for (int k = 0; k < 4; ++k) p[k] = base + (size_t)(uint32_t)(i0 + rl[k]) * ldb;
   }
 }
+__device__ __forceinline__ void row_ptrs2(const RowSrc& s, int b, int i0, const int (&rl)[2], int cofs, const char* (&p)[2]) {
+  const char* base = src_sample_base(s, b) + 4 * cofs;
+  const size_t ldb = 4 * (size_t)s.ld;
+  if (src_gathered(s.kind)) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) p[k] = base + (size_t)(uint32_t)__ldg(s.idx + i0 + rl[k]) * ldb;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) p[k] = base + (size_t)(uint32_t)(i0 + rl[k]) * ldb;
+  }
+}
 // my 16 values at byte offset `off` (a compile-time constant at every call site) from the row pointers: 4 LDG.128.
 // Fragment index of (row k, column c of my four): 8 (k >> 1) + 4 (c >> 1) + 2 (k & 1) + (c & 1).
 __device__ __forceinline__ void ldfrag4(const char* const (&p)[4], int off, float (&o)[16]) {
@@ -252,6 +263,33 @@ __device__ __forceinline__ void ldfrag4(const char* const (&p)[4], int off, floa
   for (int k = 0; k < 4; ++k) {
     const int i = 8 * (k >> 1) + 2 * (k & 1);
     o[i] = t[k].x, o[i + 1] = t[k].y, o[i + 4] = t[k].z, o[i + 5] = t[k].w;
+  }
+}
+// 8 consecutive floats (32-byte aligned) in one 256-bit load: four adjacent lanes cover one full 128-byte line
+__device__ __forceinline__ void ld256(const char* p, float* o) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+               : "l"(p));
+}
+// ldfrag4 for a source whose consecutive rows often repeat (the addend gathered through the SORTED target index: ~7 edges per
+// node): a row equal to the one before it is not loaded again (`ld` bit k = row k differs from row k-1; bit 0 is always set);
+// fixrep4, called where the fragment is consumed, copies the row that was loaded.  Saves ~2/3 of this source's L1 wavefronts.
+template <int OFF>
+__device__ __forceinline__ void ldfrag4_rep(const char* const (&p)[4], float (&o)[16], uint32_t ld) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 8 * (k >> 1) + 2 * (k & 1);
+    if (ld & (1u << k)) {  // (a predicated load: the registers of a row that is not loaded keep whatever they held)
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p[k] + OFF));
+      o[i] = t.x, o[i + 1] = t.y, o[i + 4] = t.z, o[i + 5] = t.w;
+    }
+  }
+}
+__device__ __forceinline__ void fixrep4(float (&o)[16], uint32_t ld) {
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    const int i = 8 * (k >> 1) + 2 * (k & 1), j = 8 * ((k - 1) >> 1) + 2 * ((k - 1) & 1);
+    if (!(ld & (1u << k))) o[i] = o[j], o[i + 1] = o[j + 1], o[i + 4] = o[j + 4], o[i + 5] = o[j + 5];
   }
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -284,6 +322,34 @@ __device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)
       } else {
         const __nv_bfloat162 bb = __floats2bfloat162_rn(a0, a1);
         sts32(addr, *reinterpret_cast<const uint32_t*>(&bb));
+      }
+    }
+}
+
+// Stage-0 operand store.  Stage 0 does not touch the accumulator, so its thread mapping is chosen for the memory system alone
+// (see stage0_fast): v = two rows x 8 consecutive LOGICAL features n0 .. n0+7 (n0 a multiple of 8).  In accumulator order (perm16)
+// features n0+{2j, 2j+1} and n0+{4+2j, 5+2j} are the adjacent half2 pairs at byte 8 ((n0 >> 3) & 1) of 16-byte chunk (n0 >> 4) * 2 + j:
+// one 64-bit store per (row, j, hi / lo).  `sa` = shared address of (my first row, chunk j = 0) inside the slot; j = 1 is sa ^ 16,
+// my second row is 8 operand rows (1 KB) further.
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
+template <bool SPLIT>
+__device__ __forceinline__ void store_operand_s0(uint32_t sa, const float (&v)[16], float& amax) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float a0 = v[8 * kk + 2 * j], a1 = v[8 * kk + 2 * j + 1], b0 = v[8 * kk + 4 + 2 * j], b1 = v[8 * kk + 5 + 2 * j];
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(b0), fabsf(b1))));
+      const uint32_t addr = (j ? (sa ^ 16u) : sa) + 1024u * kk;
+      if (SPLIT) {
+        const __half2 ha = __floats2half2_rn(a0, a1), hb = __floats2half2_rn(b0, b1);
+        const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+        const __half2 la = __floats2half2_rn(a0 - fa.x, a1 - fa.y), lb = __floats2half2_rn(b0 - fb.x, b1 - fb.y);
+        sts64(addr, *reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+        sts64(addr + A_HALF_BYTES, *reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+      } else {
+        const __nv_bfloat162 ba = __floats2bfloat162_rn(a0, a1), bb = __floats2bfloat162_rn(b0, b1);
+        sts64(addr, *reinterpret_cast<const uint32_t*>(&ba), *reinterpret_cast<const uint32_t*>(&bb));
       }
     }
 }
@@ -498,8 +564,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     const int cofs = 16 * hq + 4 * lc;  // my first (logical) column inside a 64-column chunk; the operand position uses 2 * lc
     const float* scl = reinterpret_cast<const float*>(smem + OFF_SCL);
     const float a0scale = scl[2 * PAR_LAYERS];
-    float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
-    float* ln_y = ln_x + WSPLIT * 128;
+    // Row statistics of a LayerNorm are exchanged between the four warps of a lane quadrant through ln_x / ln_y with ONE named
+    // barrier: consecutive LayerNorms alternate between two generations of the buffers, so a warp that runs ahead into LayerNorm
+    // i+1 writes the other generation, and it cannot reach LayerNorm i+2 (the same generation again) before every warp of the
+    // quadrant has passed the barrier of i+1, i.e. has finished reading generation i.
+    float* const ln_base = reinterpret_cast<float*>(smem + OFF_LN);
+    uint32_t ln_gen = 0;
     uint32_t fi = 0, li = 0;
     float amax = 0.f;
     Tracer tr;
@@ -575,9 +645,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     const bool l0_g0 = src_gathered(ch.layer[0].add[0].kind), l0_g1 = src_gathered(ch.layer[0].add[1].kind);
 
     // ---- stage 0, lean path: NC0 + NC1 64-column chunks from one or two aligned sources, fully unrolled ------------------------
-    // The rows stream from HBM (edge state) or L2 (node state): up to four chunks (16 x LDG.128 per thread) are in flight before
+    // Thread mapping: stage 0 never sees the accumulator, so it is laid out for the load path, not for the TMEM fragment.  The L1
+    // pipeline spends ~2 cycles per (load instruction x 128-byte line it touches) (tools/micro/ldg_wavefront.cu: 35 B/cycle/SM with
+    // the fragment's 8 rows x 64 B per LDG.128, 58 B/cycle/SM with full lines), so a warp reads FULL lines: LDG.256, four adjacent
+    // lanes = one line, 8 rows per instruction.  Warp w owns rows 32 (w & 3) + 4 (lane / 4) + 2 ((w >> 2) & 1) + {0, 1} and the
+    // 128-byte half (w >> 3) of every 64-column chunk; the 8 rows of one instruction are 4 apart, so their operand rows (TMEM
+    // lanes 32 q + 8 k + lane/4, k = row % 4) differ in their low three bits and the swizzled 64-bit stores are conflict-free.
+    // The rows stream from HBM (edge state) or L2 (node state): up to four chunks (8 x LDG.256 per thread) are in flight before
     // the first one is converted, so a tile pays the memory latency once, not once per chunk.  GBR: the operand is
     // relu(gathered row + broadcast row); the two tables are kept apart until the chunk is converted (two chunks in flight).
+    const int s0_q = warp & 3, s0_k = (warp >> 2) & 1, s0_l = warp >> 3;
+    const int s0_cofs = 32 * s0_l + 8 * lc;  // my first (logical) column inside a 64-column chunk
+    const uint32_t s0_sa = sbase + OFF_A + (32 * s0_q + 16 * s0_k + lr) * 128 + 8 * (lc & 1) + (((4 * s0_l + 2 * (lc >> 1)) ^ lr) << 4);
     auto stage0_fast = [&](auto NC0c, auto NC1c, auto GBRc, int tile) {
       constexpr int NC0 = decltype(NC0c)::value, NC1 = decltype(NC1c)::value, NC = NC0 + NC1;
       constexpr bool GBR = decltype(GBRc)::value != 0;
@@ -587,7 +666,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       int rl[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
-      // gather rows of layer 0's addends: requested first, parked in shared memory once the operand loads are under way
+      // gather rows of layer 0's addends (for the rows of my ACCUMULATOR fragment): requested first, parked in shared memory once
+      // the operand loads are under way
       uint32_t g0[4] = {0u, 0u, 0u, 0u}, g1[4] = {0u, 0u, 0u, 0u};
       if (l0_add0) {
 #pragma unroll
@@ -597,14 +677,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 #pragma unroll
         for (int k = 0; k < 4; ++k) g1[k] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
       }
-      const char* pa[4];
-      const char* pb[4] = {nullptr, nullptr, nullptr, nullptr};  // second source, or the broadcast table of GBR
-      row_ptrs(ch.a0[0], bs, i0, rl, cofs, pa);
+      int r2[2];  // my two stage-0 rows
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) r2[kk] = min(32 * s0_q + 4 * lr + 2 * s0_k + kk, nvalid - 1);
+      const char* pa[2];
+      const char* pb[2] = {nullptr, nullptr};  // second source, or the broadcast table of GBR
+      row_ptrs2(ch.a0[0], bs, i0, r2, s0_cofs, pa);
       if constexpr (GBR) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pb[k] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + rl[k]) * (size_t)ch.a0[0].ld2 + cofs);
+        for (int kk = 0; kk < 2; ++kk) pb[kk] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + r2[kk]) * (size_t)ch.a0[0].ld2 + s0_cofs);
       } else if constexpr (NC1 > 0) {
-        row_ptrs(ch.a0[1], bs, i0, rl, cofs, pb);
+        row_ptrs2(ch.a0[1], bs, i0, r2, s0_cofs, pb);
       }
       float buf[DEPTH][16] = {};
       float bufb[GBR ? DEPTH : 1][16] = {};
@@ -612,12 +695,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         constexpr int c = decltype(cc)::value;
         if (ABL3(ABL_LOADS)) return;
         if constexpr (GBR) {
-          ldfrag4(pa, 256 * c, buf[c % DEPTH]);
-          ldfrag4(pb, 256 * c, bufb[c % DEPTH]);
+          ld256(pa[0] + 256 * c, buf[c % DEPTH]), ld256(pa[1] + 256 * c, buf[c % DEPTH] + 8);
+          ld256(pb[0] + 256 * c, bufb[c % DEPTH]), ld256(pb[1] + 256 * c, bufb[c % DEPTH] + 8);
         } else if constexpr (c < NC0) {
-          ldfrag4(pa, 256 * c, buf[c % DEPTH]);
+          ld256(pa[0] + 256 * c, buf[c % DEPTH]), ld256(pa[1] + 256 * c, buf[c % DEPTH] + 8);
         } else {
-          ldfrag4(pb, 256 * (c - NC0), buf[c % DEPTH]);
+          ld256(pb[0] + 256 * (c - NC0), buf[c % DEPTH]), ld256(pb[1] + 256 * (c - NC0), buf[c % DEPTH] + 8);
         }
       };
       tr.ev(480);
@@ -643,9 +726,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         if (a0scale != 1.f) {  // (two copies of the conversion: see layer_fast)
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
-          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
+          if (!ABL3(ABL_CONVERT)) store_operand_s0<SPLIT>(s0_sa + slot * A_SLOT_BYTES, cur, amax);
         } else {
-          if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, cur, amax);
+          if (!ABL3(ABL_CONVERT)) store_operand_s0<SPLIT>(s0_sa + slot * A_SLOT_BYTES, cur, amax);
         }
         publish(slot);
         if constexpr (c + DEPTH < NC) fetch(ic<c + DEPTH>{});  // refill the buffer just consumed
@@ -699,11 +782,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
       }
       const bool ld_on = !ABL3(ABL_LOADS);
+      uint32_t ld1 = 15u;  // which rows of addend 1 differ from the row before (the others repeat it and are not loaded)
+      if constexpr (has_add1) ld1 = 1u | (p1[1] != p1[0] ? 2u : 0u) | (p1[2] != p1[1] ? 4u : 0u) | (p1[3] != p1[2] ? 8u : 0u);
       if constexpr (has0 && !has_ln) {
         if (ld_on) ldfrag4(p0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
       }
       if constexpr (has_add1) {
-        if (ld_on) ldfrag4(p1, 0, pf1);
+        if (ld_on) ldfrag4_rep<0>(p1, pf1, ld1);
       }
       // targets of my rows (fused per-target sums): requested before the accumulator wait / the statistics pass
       int dseg[4] = {0, 0, 0, 0}, dprev_q = 0;
@@ -766,6 +851,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               m2[k] = (m2[k] + qb) + d * d * (o == 1 ? 2.0f * NP : 4.0f * NP);
             }
           }
+          float* const ln_x = ln_base + (ln_gen & 1u) * (2 * WSPLIT * 128);
+          float* const ln_y = ln_x + WSPLIT * 128;
+          ++ln_gen;
           if (lc == 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
@@ -787,7 +875,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             const float rstd = 1.0f / sqrtf(q2 * (1.0f / (64.0f * NP)) + 1e-5f);
             rs[k] = rstd, sh[k] = -mu * rstd;
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
           tr.ev(2003);
         } else if constexpr (has0) {
           if (ld_on) ldfrag4(p0, 0, pf0);
@@ -836,23 +923,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         inner_any = __any_sync(0xffffffffu, (b1 && b0) || (b2 && (b0 || b1)) || (b3 && (b0 || b1 || b2)));
       }
       // The accumulator chunk s+1 is fetched from TMEM while chunk s is processed.
-      float vb[2][16] = {};
+      constexpr bool TM2 = true;  // (false: fetch each chunk when it is needed -- frees 16 registers; no measurable difference)
+      float vb[TM2 ? 2 : 1][16] = {};
       if constexpr (has_ln) tr.ev(2004);
-      if (!ABL3(ABL_TMEM)) {
+      if (TM2 && !ABL3(ABL_TMEM)) {
         tmem_ld_16x256b_x2(taddr, vb[0]);
         tmem_ld_16x256b_x2(taddr + (16u << 16), vb[0] + 8);
       }
       static_for<0, NP>([&](auto sc_) {
         constexpr int s = decltype(sc_)::value;
-        float(&v)[16] = vb[s & 1];
+        float(&v)[16] = vb[TM2 ? (s & 1) : 0];
+        if constexpr (!TM2) {
+          if (!ABL3(ABL_TMEM)) {
+            tmem_ld_16x256b_x2(taddr + 64 * s, v);
+            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+          }
+        }
         tmem_wait_ld_into(v);
         if constexpr (has_ln) tr.ev(2010 + s);
-        if constexpr (s + 1 < NP) {
+        if constexpr (TM2 && s + 1 < NP) {
           if (!ABL3(ABL_TMEM)) {
             tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vb[(s + 1) & 1]);
             tmem_ld_16x256b_x2(taddr + 64 * (s + 1) + (16u << 16), vb[(s + 1) & 1] + 8);
           }
-        } else {  // my last read of this accumulator
+        }
+        if constexpr (s + 1 == NP) {  // my last read of this accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
@@ -868,6 +963,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         if constexpr (has_add1) {
           if (ld_on) {
+            fixrep4(pf1, ld1);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += pf1[i];
           }
@@ -896,7 +992,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             if (ld_on) ldfrag4(p0, 256 * (s + 1), pf0);
           }
           if constexpr (has_add1) {
-            if (ld_on) ldfrag4(p1, 256 * (s + 1), pf1);
+            if (ld_on) ldfrag4_rep<256 * (s + 1)>(p1, pf1, ld1);
           }
         }
         if constexpr (has_out) {
@@ -1106,6 +1202,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             }
             nn *= 2.f;
           }
+          float* const ln_x = ln_base + (ln_gen & 1u) * (2 * WSPLIT * 128);
+          float* const ln_y = ln_x + WSPLIT * 128;
+          ++ln_gen;
           if (lc == 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
@@ -1129,7 +1228,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             mean[k] = mu;
             rstd[k] = 1.0f / sqrtf(q2 / (float)nval + 1e-5f);
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // ln_x / ln_y may be rewritten by the next LayerNorm
         }
 
         for (int s = 0; s < np; ++s) {
@@ -1294,6 +1392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 }  // namespace t3
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 static bool simple_kind(int k) { return k == SRC_STREAM || k == SRC_BCAST || k == SRC_GATHER || k == SRC_BGATHER; }
 // a source every thread may read with 8-byte loads over `need` columns
 // byte offsets inside a fast-path source fit 32 bits: gathered rows are addressed relative to the sample, contiguous rows
@@ -1318,8 +1417,8 @@ static void tc3_mark_lean(TcChain& ch) {
       const RowSrc& s = ch.a0[a];
       if (s.kind == SRC_NONE) continue;
       const bool gbr = s.kind == SRC_GATHER_BCAST_RELU;
-      ok = ok && (simple_kind(s.kind) || gbr) && aligned16(s.base + s.col0) && !(s.ld & 3);
-      if (gbr) ok = ok && aligned16(s.base2) && !(s.ld2 & 3);
+      ok = ok && (simple_kind(s.kind) || gbr) && aligned32(s.base + s.col0) && !(s.ld & 7);  // 256-bit loads
+      if (gbr) ok = ok && aligned32(s.base2) && !(s.ld2 & 7);
       wsum += s.width;
     }
     const bool two = ch.a0[1].kind != SRC_NONE;
