@@ -129,7 +129,7 @@ struct gw_plan {
   DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
   size_t total_bytes = 0;
   // tensor-core path: packed weight images (UMMA operand layout) and their descriptors
-  struct TcW { const void* p = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; float gain = 0.f; };  // gain = K * max|W|: |A.W^T| <= gain * max|A|
+  struct TcW { const void* p = nullptr; const void* p32 = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; float gain = 0.f; };  // gain = K * max|W|: |A.W^T| <= gain * max|A|
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
@@ -294,7 +294,7 @@ static bool is_tc(const gw_plan* p) { return p->d.precision != GW_PREC_FP32_SIMT
 // layer = Linear `w` (+ bias b[l] of MLP m when l >= 0) (+ ReLU); magnitudes for the operand-range ladder travel along
 static TcLayer tc_layer(const gw_plan::TcW& w, const Mlp* m, int l, bool relu, bool feeds) {
   TcLayer L;
-  L.Wp = w.p, L.K = w.K, L.N = w.N, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
+  L.Wp = w.p, L.Wp32 = w.p32, L.K = w.K, L.N = w.N, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
   L.bias = (m && l >= 0) ? m->b[l] : nullptr, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
   L.gain = w.gain, L.off = (m && l >= 0 && (size_t)l < m->bmax.size()) ? m->bmax[l] : 0.f;
   return L;
@@ -491,7 +491,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
   size_t total = 0;
   for (size_t i = 0; i < n; ++i) {
     GW_CUDA(launch_absmax(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, p->tc_absmax.p + i, st));
-    total += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
+    total += 2 * ((tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024);  // two images: perm16 and perm32 feature order
   }
   for (size_t i = 0; i < nv; ++i) GW_CUDA(launch_absmax(vreqs[i].v, vreqs[i].n, vreqs[i].n, 1, p->tc_absmax.p + n + i, st));
   std::vector<float> amax(n + nv);
@@ -514,14 +514,17 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
       scale = std::ldexp(1.f, 12 - e);   // amax * scale in [2048, 4096)
     }
     void* dst = p->tc_packed.p + off;
+    const size_t img = (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
     GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, 1, dst, st));
+    GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, 2, static_cast<unsigned char*>(dst) + img, st));
     reqs[i].out->p = dst;
+    reqs[i].out->p32 = static_cast<unsigned char*>(dst) + img;
     reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
     reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
     reqs[i].out->n_valid = reqs[i].N;
     reqs[i].out->winv = 1.f / scale;
     reqs[i].out->gain = (float)reqs[i].K * amax[i];
-    off += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
+    off += 2 * img;
   }
   return 0;
 }
@@ -1129,7 +1132,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   const bool tc = d.precision != GW_PREC_FP32_SIMT;
   const size_t n_io = std::max((size_t)d.n_in, (size_t)d.n_out);
   const size_t dec_tiles = ((size_t)d.n_dec_edges + 127) / 128, lat_tiles = ((size_t)d.n_lat_edges + 127) / 128;
-  const size_t per_sample = tc ? (n_io * Dn + (size_t)d.n_in * De + (size_t)d.n_out * De + dec_tiles * 1024) * sizeof(float)
+  const size_t per_sample = tc ? (n_io * Dn + (size_t)d.n_in * De + (size_t)d.n_out * De + dec_tiles * 2048) * sizeof(float)
                                : (2 * max_rows * max_hid + std::max((size_t)d.n_in, (size_t)d.n_dec_edges) * De + n_io * Dn) * sizeof(float);
   size_t chunk = std::max<size_t>(1, std::min<size_t>(d.max_batch, (48ull << 30) / std::max<size_t>(per_sample, 1)));
   if (const char* force = getenv("GW_B200_CHUNK")) {  // test knob: exercise the chunked stage loops on small grids
@@ -1169,7 +1172,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   }
   if (tc) {
     rc |= p->agg_grid.alloc(chunk * d.n_out * De);
-    rc |= p->seg_carry.alloc(std::max(chunk * dec_tiles, B * (lat_tiles + 1)) * 1024);
+    rc |= p->seg_carry.alloc(std::max(chunk * dec_tiles, B * (lat_tiles + 1)) * 2048);  // [samples][tiles][8 row groups][256]
   }
   if (rc) {
     std::string keep = gw::g_err;

@@ -43,8 +43,8 @@ cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream);
 // Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with
 // cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts).
 size_t tc_packed_bytes(int K_src, int N_src, int parts);
-cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm16, void* dst,
-                                cudaStream_t stream);  // perm16: feature order of gw_tc3.cu (gw_pack.cu)
+cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm, void* dst,
+                                cudaStream_t stream);  // perm: 1 = perm16 (general path), 2 = perm32 (lean path) feature order of gw_tc3.cu (gw_pack.cu)
 cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream);
 
 // device-side observation graph of the assimilator (gw_graph.cu)

@@ -64,7 +64,8 @@ struct GemmOp {
 constexpr int TC_MAX_LAYERS = 8;
 
 struct TcLayer {
-  const void* Wp = nullptr;   // packed weights (gw_pack.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major
+  const void* Wp = nullptr;   // packed weights (gw_pack.cu): [K/64][parts][N x 64] fp16/bf16, UMMA SW128 K-major, perm16 feature order
+  const void* Wp32 = nullptr; // the same weights in perm32 feature order (lean path of gw_tc3.cu); the launcher picks
   int32_t K = 0, N = 0;       // K multiple of 64 (zero padded), N multiple of 16 (<= 256)
   int32_t n_valid = 0;        // real output columns (<= N); bias / LN parameters / addends exist only for these
   float wscale_inv = 1.f;     // weights are stored times a power of two; the accumulator is multiplied by this
@@ -85,11 +86,11 @@ struct TcLayer {
   float ln_bound = 0.f;       // LayerNorm layers: sqrt(N) * max|gamma| + max|beta| bounds the normalised row
   float* out_bound = nullptr; // device float the kernel sets to the bound of this layer's result (CTA 0), for `out` consumers
   // fused per-target sum of the result rows (graph_net_block.py:188 scatter_sum): rows are grouped by target (seg_dst
-  // non-decreasing, segments of <= 8 rows); each complete segment sum goes to seg_out, pieces cut by a 32-row quadrant
-  // boundary go to seg_carry and are added by gw_seg_carry_kernel.
+  // non-decreasing, segments of <= 8 rows); each segment sum goes to seg_out, the part of a segment behind a 16-row group
+  // boundary (the rows one worker warp reduces) goes to seg_carry and is added by gw_seg_carry_kernel.
   const int32_t* seg_dst = nullptr;  // [rows_per_sample] target of every row
   float* seg_out = nullptr;          // [(b * seg_rows + target) * seg_ld + n]
-  float* seg_carry = nullptr;        // [((b * tiles_per_sample + tile) * 4 + quadrant) * 256 + n]
+  float* seg_carry = nullptr;        // [((b * tiles_per_sample + tile) * 8 + row group) * 256 + n]
   int32_t seg_ld = 0, seg_rows = 0;
   float seg_maxdeg = 0.f;            // longest segment (bound of the sums)
   float* seg_bound = nullptr;        // device float set to the bound of the segment sums

@@ -1,6 +1,7 @@
 // gw_pack.cu -- one-off packing of nn.Linear weights into the operand images the tensor-core chain kernel (gw_tc3.cu) streams:
 // fp16 hi|lo (fp32-faithful mode) or bf16, K-major, SWIZZLE_128B, one contiguous panel per 64-wide K chunk, power-of-two
-// pre-scaled, output rows and K columns permuted inside every group of 16 (perm16, see gw_tc3.cu).
+// pre-scaled, output rows and K columns permuted inside every group of 16 (perm16) or 32 (perm32) -- the two feature orders of the
+// chain kernel's general and lean paths, see gw_tc3.cu.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -22,12 +23,18 @@ size_t tc_packed_bytes(int K_src, int N_src, int parts) {
 // perm16 (gw_tc3.cu): inside every group of 16 output rows and of 16 K columns, packed position a holds logical index
 // f(a) = 4*((a>>1)&3) + 2*(a>>3) + (a&1), the order in which a tcgen05.ld.16x256b fragment gives each thread 4 consecutive features.
 __host__ __device__ inline int perm16_f(int a) { return (a & ~15) | (4 * ((a >> 1) & 3) + 2 * ((a >> 3) & 1) + (a & 1)); }
+// perm32 (lean path, tcgen05.ld.16x256b.x4 fragments: a thread owns 8 consecutive features of a row): inside every group of 32,
+// packed position a = 8g + 2c + e holds logical index 8c + 2g + e.
+__host__ __device__ inline int perm32_f(int a) { return (a & ~31) | (8 * ((a >> 1) & 3) + 2 * ((a >> 3) & 3) + (a & 1)); }
 __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int K_src, int N_src, int Kp, int Np,
-                                       float wscale, int parts, int perm16, uint8_t* __restrict__ dst) {
+                                       float wscale, int parts, int perm, uint8_t* __restrict__ dst) {
   const size_t total = (size_t)Np * Kp;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(e / Kp), k = (int)(e % Kp);
-    const int ns = perm16 ? perm16_f(n) : n, ks = perm16 ? perm16_f(k) : k;
+    // perm: 0 none, 1 perm16, 2 perm32 (rows: only when the padded row count is a multiple of 32 -- else perm16, which then is
+    // the last layer of a chain; K is always a multiple of 64)
+    const int ns = perm == 2 ? ((Np & 31) ? perm16_f(n) : perm32_f(n)) : (perm ? perm16_f(n) : n);
+    const int ks = perm == 2 ? perm32_f(k) : (perm ? perm16_f(k) : k);
     const float w = (ns < N_src && ks < K_src) ? W[(size_t)ns * ldw + ks] * wscale : 0.f;
     const int kc = k >> 6, kk = k & 63;
     const size_t panel = (size_t)Np * 128;
@@ -43,10 +50,10 @@ __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int
   }
 }
 
-cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm16, void* dst,
+cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm, void* dst,
                                 cudaStream_t stream) {
   const int Kp = round_up(K_src, 64), Np = round_up(N_src, 16);
-  gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, perm16, static_cast<uint8_t*>(dst));
+  gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, perm, static_cast<uint8_t*>(dst));
   count_launch();
   return cudaGetLastError();
 }

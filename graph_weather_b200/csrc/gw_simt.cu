@@ -614,16 +614,17 @@ cudaError_t launch_csr_expand(const int32_t* ptr, int n, int32_t* dst, int* stat
   count_launch();
   return cudaGetLastError();
 }
-// A segment cut by a 32-row quadrant boundary of the chain kernel's tiles left the sum of its later rows in `carry`
-// ([batch][tiles][4][256]); add it to the segment's row of out.  One 64-thread CTA per (boundary, sample); fixed order.
+// A segment cut by a 16-row group boundary of the chain kernel's tiles (the rows one worker warp reduces, gw_tc3.cu) left the
+// sum of its later rows in `carry` ([batch][tiles][8][256]); add it to the segment's row of out.  One 64-thread CTA per
+// (boundary, sample); fixed order.
 __global__ void __launch_bounds__(64) gw_seg_carry_kernel(const float* __restrict__ carry, const int32_t* __restrict__ seg_dst, int rows,
                                                           int tiles, int seg_rows, float* __restrict__ out, int ldo) {
-  const int bq = blockIdx.x, b = blockIdx.y;  // boundary = tile * 4 + quadrant
-  const int r = (bq >> 2) * 128 + (bq & 3) * 32;
+  const int bg = blockIdx.x, b = blockIdx.y;  // boundary = tile * 8 + group
+  const int r = (bg >> 3) * 128 + (bg & 7) * 16;
   if (r <= 0 || r >= rows) return;
   const int d = __ldg(seg_dst + r);
-  if (__ldg(seg_dst + r - 1) != d) return;  // the quadrant starts a new segment: nothing was carried
-  const float4 c = __ldg(reinterpret_cast<const float4*>(carry + ((size_t)b * tiles * 4 + bq) * 256 + threadIdx.x * 4));
+  if (__ldg(seg_dst + r - 1) != d) return;  // the group starts a new segment: nothing was carried
+  const float4 c = __ldg(reinterpret_cast<const float4*>(carry + ((size_t)b * tiles * 8 + bg) * 256 + threadIdx.x * 4));
   float4* o = reinterpret_cast<float4*>(out + ((size_t)b * seg_rows + d) * (size_t)ldo + threadIdx.x * 4);
   float4 v = *o;
   v.x += c.x, v.y += c.y, v.z += c.z, v.w += c.w;
@@ -633,7 +634,7 @@ cudaError_t launch_seg_carry(const float* carry, const int32_t* seg_dst, int row
                              cudaStream_t stream) {
   if (rows <= 0 || batch <= 0) return cudaSuccess;
   const int tiles = (rows + 127) / 128;
-  gw_seg_carry_kernel<<<dim3(tiles * 4, batch), 64, 0, stream>>>(carry, seg_dst, rows, tiles, seg_rows, out, ldo);
+  gw_seg_carry_kernel<<<dim3(tiles * 8, batch), 64, 0, stream>>>(carry, seg_dst, rows, tiles, seg_rows, out, ldo);
   count_launch();
   return cudaGetLastError();
 }

@@ -92,8 +92,8 @@ constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_PAR = OFF_TMEM + 16;                // float bias[PAR_LAYERS][256]
 constexpr int OFF_LNP = OFF_PAR + PAR_LAYERS * 1024;  // float gamma_beta[2][2][256]
 constexpr int OFF_LN = OFF_LNP + 4 * 1024;            // float ln_xy[2][2][WSPLIT][128]: row statistics exchange (mean, M2), two generations
-constexpr int OFF_PRE = OFF_LN + 2 * 2 * WSPLIT * 128 * 4;  // uint32 pre[8][NUM_WORKERS]: layer-0 gather rows of the coming tile
-constexpr int OFF_SCL = OFF_PRE + 8 * NUM_WORKERS * 4;  // float scl[2 * PAR_LAYERS + 4]: per layer {accumulator scale, operand scale of the result}, then the stage-0 operand scale
+constexpr int OFF_PRE = OFF_LN + 2 * 2 * WSPLIT * 128 * 4;  // uint32 pre[4][NUM_WORKERS]: layer-0 gather rows of the coming tile (2 rows x 2 addends per thread)
+constexpr int OFF_SCL = OFF_PRE + 4 * NUM_WORKERS * 4;  // float scl[2 * PAR_LAYERS + 4]: per layer {accumulator scale, operand scale of the result}, then the stage-0 operand scale
 constexpr int SMEM_BYTES = OFF_SCL + (2 * PAR_LAYERS + 4) * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_B % 1024 == 0 && A_SLOT_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "SWIZZLE_128B needs 1 KB alignment");
@@ -109,6 +109,18 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// x4: 32 accumulator columns of 16 rows; register 4 g + 2 m + e = (row t/4 + 8 m, column 8 g + 2 (t%4) + e)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Wait for TMEM loads that were issued earlier into v (asynchronously: the compiler believes v was written by the issuing
@@ -230,18 +242,7 @@ using ic = std::integral_constant<int, V>;
 __device__ __forceinline__ const char* src_sample_base(const RowSrc& s, int b) {
   return reinterpret_cast<const char*>(s.base + (src_per_sample(s.kind) ? (size_t)b * (size_t)s.src_rows * (size_t)s.ld : (size_t)0) + s.col0);
 }
-// my four row pointers into a source: tile rows i0 + rl[k] (through the index for gathered sources), first column cofs
-__device__ __forceinline__ void row_ptrs(const RowSrc& s, int b, int i0, const int (&rl)[4], int cofs, const char* (&p)[4]) {
-  const char* base = src_sample_base(s, b) + 4 * cofs;
-  const size_t ldb = 4 * (size_t)s.ld;
-  if (src_gathered(s.kind)) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) p[k] = base + (size_t)(uint32_t)__ldg(s.idx + i0 + rl[k]) * ldb;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) p[k] = base + (size_t)(uint32_t)(i0 + rl[k]) * ldb;
-  }
-}
+// my two row pointers into a source: tile rows i0 + rl[m] (through the index for gathered sources), first column cofs
 __device__ __forceinline__ void row_ptrs2(const RowSrc& s, int b, int i0, const int (&rl)[2], int cofs, const char* (&p)[2]) {
   const char* base = src_sample_base(s, b) + 4 * cofs;
   const size_t ldb = 4 * (size_t)s.ld;
@@ -253,66 +254,46 @@ __device__ __forceinline__ void row_ptrs2(const RowSrc& s, int b, int i0, const 
     for (int k = 0; k < 2; ++k) p[k] = base + (size_t)(uint32_t)(i0 + rl[k]) * ldb;
   }
 }
-// my 16 values at byte offset `off` (a compile-time constant at every call site) from the row pointers: 4 LDG.128.
-// Fragment index of (row k, column c of my four): 8 (k >> 1) + 4 (c >> 1) + 2 (k & 1) + (c & 1).
-__device__ __forceinline__ void ldfrag4(const char* const (&p)[4], int off, float (&o)[16]) {
-  float4 t[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(p[k] + off));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = 8 * (k >> 1) + 2 * (k & 1);
-    o[i] = t[k].x, o[i + 1] = t[k].y, o[i + 4] = t[k].z, o[i + 5] = t[k].w;
-  }
-}
 // 8 consecutive floats (32-byte aligned) in one 256-bit load: four adjacent lanes cover one full 128-byte line
 __device__ __forceinline__ void ld256(const char* p, float* o) {
   asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
                : "l"(p));
 }
-// ldfrag4 for a source whose consecutive rows often repeat (the addend gathered through the SORTED target index: ~7 edges per
-// node): a row equal to the one before it is not loaded again (`ld` bit k = row k differs from row k-1; bit 0 is always set);
-// fixrep4, called where the fragment is consumed, copies the row that was loaded.  Saves ~2/3 of this source's L1 wavefronts.
-template <int OFF>
-__device__ __forceinline__ void ldfrag4_rep(const char* const (&p)[4], float (&o)[16], uint32_t ld) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = 8 * (k >> 1) + 2 * (k & 1);
-    if (ld & (1u << k)) {  // (a predicated load: the registers of a row that is not loaded keep whatever they held)
-      const float4 t = __ldg(reinterpret_cast<const float4*>(p[k] + OFF));
-      o[i] = t.x, o[i + 1] = t.y, o[i + 4] = t.z, o[i + 5] = t.w;
-    }
-  }
+__device__ __forceinline__ void st256(char* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+               : "memory");
 }
-__device__ __forceinline__ void fixrep4(float (&o)[16], uint32_t ld) {
-#pragma unroll
-  for (int k = 1; k < 4; ++k) {
-    const int i = 8 * (k >> 1) + 2 * (k & 1), j = 8 * ((k - 1) >> 1) + 2 * ((k - 1) & 1);
-    if (!(ld & (1u << k))) o[i] = o[j], o[i + 1] = o[j + 1], o[i + 4] = o[j + 4], o[i + 5] = o[j + 5];
-  }
-}
+// Lean-path fragment (tcgen05.ld.16x256b.x4, perm32): index 4 g + 2 m + e = (row m of my two, feature 2 g + e of my eight).
+// FR(m, t): fragment index of (row m, feature t); PX(i): row-order index 8 m + t of fragment index i.
+__host__ __device__ constexpr int FR(int m, int t) { return 4 * (t >> 1) + 2 * m + (t & 1); }
+__host__ __device__ constexpr int PX(int i) { return 8 * ((i >> 1) & 1) + 2 * (i >> 2) + (i & 1); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// v[i] = v[i] * s + b(column of i)   (bias / LayerNorm parameter vectors are float4 per thread)
-__device__ __forceinline__ float col4(const float4& b, int i) { return ((i >> 2) & 1) ? ((i & 1) ? b.w : b.z) : ((i & 1) ? b.y : b.x); }
-// Operand store with precomputed addressing.  `sa` = shared address of (my row 32q + lane/4, my half2, chunk j = 0) inside the
-// slot; the j = 1 chunk is sa ^ 16 (SWIZZLE_128B flips bit 4), my other rows are +8 / +16 / +24 rows = immediates.
+// column parameter (bias / LayerNorm gamma, beta: my 8 features as two float4) of fragment index i
+__device__ __forceinline__ float col8(const float4& lo, const float4& hi, int i) {
+  const int c = 2 * (i >> 2) + (i & 1);
+  const float4& b = (c & 4) ? hi : lo;
+  return (c & 2) ? ((c & 1) ? b.w : b.z) : ((c & 1) ? b.y : b.x);
+}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-template <bool SPLIT>
-__device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)[16], float& amax) {
-  const uint32_t sa1 = sa ^ 16u;
+// Lean-path operand store.  Value (row m, feature t = 2 g + e of my eight) is accumulator column 32 fc + 8 g + 2 (lane % 4) + e of
+// the 64-column chunk: half2 (e = 0, 1) at byte 4 (lane % 4) of 16-byte chunk 4 fc + g, swizzled with the operand row's low bits
+// (= lane / 4).  `sa` = shared address of (my first row, g = 0) inside the slot: g flips bits 4-5, my second row is 8 operand
+// rows (1 KB) further.  ROWORDER: v is in row order (stage 0) instead of fragment order (epilogues).
+template <bool SPLIT, bool ROWORDER>
+__device__ __forceinline__ void store_operand_x4(uint32_t sa, const float (&v)[16], float& amax) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int i = 8 * (k >> 1) + 4 * j + 2 * (k & 1);
+    for (int g = 0; g < 4; ++g) {
+      const int i = ROWORDER ? 8 * m + 2 * g : 4 * g + 2 * m;
       const float a0 = v[i], a1 = v[i + 1];
       amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
-      const uint32_t addr = (j ? sa1 : sa) + (16 * (k >> 1) + 8 * (k & 1)) * 128;
+      const uint32_t addr = (sa ^ (uint32_t)(g << 4)) + 1024u * m;
       if (SPLIT) {
         const __half2 hh = __floats2half2_rn(a0, a1);
         const float2 hf = __half22float2(hh);
@@ -322,34 +303,6 @@ __device__ __forceinline__ void store_operand_fast(uint32_t sa, const float (&v)
       } else {
         const __nv_bfloat162 bb = __floats2bfloat162_rn(a0, a1);
         sts32(addr, *reinterpret_cast<const uint32_t*>(&bb));
-      }
-    }
-}
-
-// Stage-0 operand store.  Stage 0 does not touch the accumulator, so its thread mapping is chosen for the memory system alone
-// (see stage0_fast): v = two rows x 8 consecutive LOGICAL features n0 .. n0+7 (n0 a multiple of 8).  In accumulator order (perm16)
-// features n0+{2j, 2j+1} and n0+{4+2j, 5+2j} are the adjacent half2 pairs at byte 8 ((n0 >> 3) & 1) of 16-byte chunk (n0 >> 4) * 2 + j:
-// one 64-bit store per (row, j, hi / lo).  `sa` = shared address of (my first row, chunk j = 0) inside the slot; j = 1 is sa ^ 16,
-// my second row is 8 operand rows (1 KB) further.
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
-template <bool SPLIT>
-__device__ __forceinline__ void store_operand_s0(uint32_t sa, const float (&v)[16], float& amax) {
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float a0 = v[8 * kk + 2 * j], a1 = v[8 * kk + 2 * j + 1], b0 = v[8 * kk + 4 + 2 * j], b1 = v[8 * kk + 5 + 2 * j];
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(b0), fabsf(b1))));
-      const uint32_t addr = (j ? (sa ^ 16u) : sa) + 1024u * kk;
-      if (SPLIT) {
-        const __half2 ha = __floats2half2_rn(a0, a1), hb = __floats2half2_rn(b0, b1);
-        const float2 fa = __half22float2(ha), fb = __half22float2(hb);
-        const __half2 la = __floats2half2_rn(a0 - fa.x, a1 - fa.y), lb = __floats2half2_rn(b0 - fb.x, b1 - fb.y);
-        sts64(addr, *reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-        sts64(addr + A_HALF_BYTES, *reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
-      } else {
-        const __nv_bfloat162 ba = __floats2bfloat162_rn(a0, a1), bb = __floats2bfloat162_rn(b0, b1);
-        sts64(addr, *reinterpret_cast<const uint32_t*>(&ba), *reinterpret_cast<const uint32_t*>(&bb));
       }
     }
 }
@@ -635,61 +588,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       fi += nk0;
     };
 
-    // operand-store address of (my first row, chunk j = 0) inside a slot; see store_operand_fast
-    const uint32_t sa0 = sbase + OFF_A + (32 * q + lr) * 128 + 4 * lc + (((2 * hq) ^ lr) << 4);
+    // =================================== lean path (MODE 1) ================================================================
+    // One thread mapping serves stage 0 and every epilogue.  Warp (q, fh, fc) = (warp & 3, (warp >> 2) & 1, warp >> 3) covers the
+    // 16 tile rows frow = 32 q + 16 fh .. +15 and the 32 columns 32 fc .. +31 of every 64-column chunk.  A thread holds TWO
+    // CONSECUTIVE rows (logical rows fr0, fr0 + 1 <-> TMEM lanes / operand rows frow + lane/4 and + 8) times EIGHT CONSECUTIVE
+    // features fcofs .. fcofs + 7: one tcgen05.ld.16x256b.x4 under the perm32 feature order (gw_pack.cu).  Four adjacent lanes
+    // thus cover one full 128-byte line of a row, and a warp-level 256-bit access touches 8 full lines.  The L1 pipeline spends
+    // ~2 cycles per (instruction x line touched) (tools/micro/ldg_wavefront.cu: 35 B/cycle/SM with the x2 fragment's 8 rows x 64 B
+    // per LDG.128, 58 B/cycle/SM with full lines), and the rows gathered through the sorted target index coalesce further (the
+    // 8 rows of one instruction are 16 consecutive edges: ~3 distinct targets).  The 8 rows of an instruction are operand rows
+    // frow + 0..7 (+8): their low three bits differ, so the swizzled operand stores are conflict-free.
+    const int fh = hq & 1, fc = hq >> 1;
+    const int frow = 32 * q + 16 * fh;
+    const int fr0 = frow + 2 * lr;
+    const int fcofs = 32 * fc + 8 * lc;  // my first (logical) column inside a 64-column chunk
+    const uint32_t fsa = sbase + OFF_A + (frow + lr) * 128 + 4 * lc + (((4 * fc) ^ lr) << 4);  // store_operand_x4
+    const uint32_t ftm = ((uint32_t)frow << 16) + 32 * fc;                                        // my TMEM lanes / columns
+    const int fbar = 1 + 2 * q + fh;  // named barrier of the two warps (fc = 0, 1) that share my rows
 
     // gather rows of layer 0's addends for the tile whose stage 0 ran last (resolved there, so that the index loads do
     // not sit between two tiles); kept in shared memory, one word per thread and row: registers are the scarce resource
-    uint32_t* pre_s = reinterpret_cast<uint32_t*>(smem + OFF_PRE) + threadIdx.x;  // [8][NUM_WORKERS], one column per thread
+    uint32_t* pre_s = reinterpret_cast<uint32_t*>(smem + OFF_PRE) + threadIdx.x;  // [4][NUM_WORKERS], one column per thread
     const bool l0_add0 = ch.layer[0].add[0].kind != SRC_NONE, l0_add1 = ch.layer[0].add[1].kind != SRC_NONE;
     const bool l0_g0 = src_gathered(ch.layer[0].add[0].kind), l0_g1 = src_gathered(ch.layer[0].add[1].kind);
 
     // ---- stage 0, lean path: NC0 + NC1 64-column chunks from one or two aligned sources, fully unrolled ------------------------
-    // Thread mapping: stage 0 never sees the accumulator, so it is laid out for the load path, not for the TMEM fragment.  The L1
-    // pipeline spends ~2 cycles per (load instruction x 128-byte line it touches) (tools/micro/ldg_wavefront.cu: 35 B/cycle/SM with
-    // the fragment's 8 rows x 64 B per LDG.128, 58 B/cycle/SM with full lines), so a warp reads FULL lines: LDG.256, four adjacent
-    // lanes = one line, 8 rows per instruction.  Warp w owns rows 32 (w & 3) + 4 (lane / 4) + 2 ((w >> 2) & 1) + {0, 1} and the
-    // 128-byte half (w >> 3) of every 64-column chunk; the 8 rows of one instruction are 4 apart, so their operand rows (TMEM
-    // lanes 32 q + 8 k + lane/4, k = row % 4) differ in their low three bits and the swizzled 64-bit stores are conflict-free.
     // The rows stream from HBM (edge state) or L2 (node state): up to four chunks (8 x LDG.256 per thread) are in flight before
     // the first one is converted, so a tile pays the memory latency once, not once per chunk.  GBR: the operand is
     // relu(gathered row + broadcast row); the two tables are kept apart until the chunk is converted (two chunks in flight).
-    const int s0_q = warp & 3, s0_k = (warp >> 2) & 1, s0_l = warp >> 3;
-    const int s0_cofs = 32 * s0_l + 8 * lc;  // my first (logical) column inside a 64-column chunk
-    const uint32_t s0_sa = sbase + OFF_A + (32 * s0_q + 16 * s0_k + lr) * 128 + 8 * (lc & 1) + (((4 * s0_l + 2 * (lc >> 1)) ^ lr) << 4);
     auto stage0_fast = [&](auto NC0c, auto NC1c, auto GBRc, int tile) {
       constexpr int NC0 = decltype(NC0c)::value, NC1 = decltype(NC1c)::value, NC = NC0 + NC1;
       constexpr bool GBR = decltype(GBRc)::value != 0;
       constexpr int DEPTH = GBR ? 2 : 4;
       const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
       const int nvalid = min(TILE_M, rows - i0);
-      int rl[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
-      // gather rows of layer 0's addends (for the rows of my ACCUMULATOR fragment): requested first, parked in shared memory once
-      // the operand loads are under way
-      uint32_t g0[4] = {0u, 0u, 0u, 0u}, g1[4] = {0u, 0u, 0u, 0u};
+      const int r2[2] = {min(fr0, nvalid - 1), min(fr0 + 1, nvalid - 1)};
+      // gather rows of layer 0's addends: requested first, parked in shared memory once the operand loads are under way
+      uint32_t g0[2] = {0u, 0u}, g1[2] = {0u, 0u};
       if (l0_add0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) g0[k] = l0_g0 ? (uint32_t)__ldg(ch.layer[0].add[0].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
+        for (int m = 0; m < 2; ++m) g0[m] = l0_g0 ? (uint32_t)__ldg(ch.layer[0].add[0].idx + i0 + r2[m]) : (uint32_t)(i0 + r2[m]);
       }
       if (l0_add1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) g1[k] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + rl[k]) : (uint32_t)(i0 + rl[k]);
+        for (int m = 0; m < 2; ++m) g1[m] = l0_g1 ? (uint32_t)__ldg(ch.layer[0].add[1].idx + i0 + r2[m]) : (uint32_t)(i0 + r2[m]);
       }
-      int r2[2];  // my two stage-0 rows
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) r2[kk] = min(32 * s0_q + 4 * lr + 2 * s0_k + kk, nvalid - 1);
       const char* pa[2];
       const char* pb[2] = {nullptr, nullptr};  // second source, or the broadcast table of GBR
-      row_ptrs2(ch.a0[0], bs, i0, r2, s0_cofs, pa);
+      row_ptrs2(ch.a0[0], bs, i0, r2, fcofs, pa);
       if constexpr (GBR) {
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) pb[kk] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + r2[kk]) * (size_t)ch.a0[0].ld2 + s0_cofs);
+        for (int m = 0; m < 2; ++m) pb[m] = reinterpret_cast<const char*>(ch.a0[0].base2 + (size_t)(uint32_t)(i0 + r2[m]) * (size_t)ch.a0[0].ld2 + fcofs);
       } else if constexpr (NC1 > 0) {
-        row_ptrs2(ch.a0[1], bs, i0, r2, s0_cofs, pb);
+        row_ptrs2(ch.a0[1], bs, i0, r2, fcofs, pb);
       }
-      float buf[DEPTH][16] = {};
+      float buf[DEPTH][16] = {};  // [row m][8 features]
       float bufb[GBR ? DEPTH : 1][16] = {};
       auto fetch = [&](auto cc) {
         constexpr int c = decltype(cc)::value;
@@ -705,14 +658,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       };
       tr.ev(480);
       static_for<0, (NC < DEPTH ? NC : DEPTH)>([&](auto cc) { fetch(cc); });
-      if (l0_add0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[k * NUM_WORKERS] = g0[k];
-      }
-      if (l0_add1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pre_s[(4 + k) * NUM_WORKERS] = g1[k];
-      }
+      if (l0_add0) pre_s[0] = g0[0], pre_s[NUM_WORKERS] = g0[1];
+      if (l0_add1) pre_s[2 * NUM_WORKERS] = g1[0], pre_s[3 * NUM_WORKERS] = g1[1];
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
         const uint32_t f = fi + c, slot = f % A_SLOTS, n = f / A_SLOTS;
@@ -726,9 +673,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         if (a0scale != 1.f) {  // (two copies of the conversion: see layer_fast)
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] *= a0scale;
-          if (!ABL3(ABL_CONVERT)) store_operand_s0<SPLIT>(s0_sa + slot * A_SLOT_BYTES, cur, amax);
+          if (!ABL3(ABL_CONVERT)) store_operand_x4<SPLIT, true>(fsa + slot * A_SLOT_BYTES, cur, amax);
         } else {
-          if (!ABL3(ABL_CONVERT)) store_operand_s0<SPLIT>(s0_sa + slot * A_SLOT_BYTES, cur, amax);
+          if (!ABL3(ABL_CONVERT)) store_operand_x4<SPLIT, true>(fsa + slot * A_SLOT_BYTES, cur, amax);
         }
         publish(slot);
         if constexpr (c + DEPTH < NC) fetch(ic<c + DEPTH>{});  // refill the buffer just consumed
@@ -739,7 +686,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
 
     // ---- one layer's epilogue, lean path: N = 64 NP, full-width aligned addends / residual / output ---------------------------
     // Register budget: two accumulator fragments (the chunk in work and the next one in flight from TMEM), the prefetched
-    // addend / residual fragments of the next chunk, and 8 registers of row pointers per global source.
+    // addend / residual rows of the next chunk, and 4 registers of row pointers per global source.  Accumulator fragments are in
+    // fragment order (index 4 g + 2 m + e = row m, feature 2 g + e), everything read from / written to global memory in row order
+    // (index 8 m + t); FR() / PX() translate at compile time.
     auto layer_fast = [&](auto FLc, auto NPc, int l, uint32_t acc, uint32_t use, bool waited, int tile, int ln_slot) {
       constexpr int F = decltype(FLc)::value, NP = decltype(NPc)::value;
       constexpr bool has_add0 = (F & F_ADD0) != 0, has_add1 = (F & F_ADD1) != 0, has_res = (F & F_RES) != 0, has_out = (F & F_OUT) != 0;
@@ -749,54 +698,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
       const int nvalid = min(TILE_M, rows - i0);
       const float wsi = scl[2 * l], osc = scl[2 * l + 1];
-      const uint32_t bias_a = sbase + OFF_PAR + 4 * cofs + l * 1024;
-      const uint32_t g_a = sbase + OFF_LNP + 4 * cofs + (ln_slot * 2) * 1024, b_a = g_a + 1024;
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * hq;
+      const uint32_t bias_a = sbase + OFF_PAR + 4 * fcofs + l * 1024;
+      const uint32_t g_a = sbase + OFF_LNP + 4 * fcofs + (ln_slot * 2) * 1024, b_a = g_a + 1024;
+      const uint32_t taddr = tmem_base + ftm + acc * 256;
       const RowSrc& src0 = has_add0 ? L.add[0] : L.residual;
-      const char* p0[4] = {nullptr, nullptr, nullptr, nullptr};  // addend 0 or residual rows
-      const char* p1[4] = {nullptr, nullptr, nullptr, nullptr};  // addend 1 rows
+      const char* p0[2] = {nullptr, nullptr};  // addend 0 or residual rows
+      const char* p1[2] = {nullptr, nullptr};  // addend 1 rows
       float pf0[16] = {}, pf1[16] = {};
       {
-        int rl[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rl[k] = min(re[k], nvalid - 1);
+        const int r2[2] = {min(fr0, nvalid - 1), min(fr0 + 1, nvalid - 1)};
         if constexpr (has0) {
           if (l == 0 && has_add0) {  // rows resolved during this tile's stage 0
-            const char* base = src_sample_base(src0, bs) + 4 * cofs;
+            const char* base = src_sample_base(src0, bs) + 4 * fcofs;
             const size_t ldb = 4 * (size_t)src0.ld;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p0[k] = base + (size_t)pre_s[k * NUM_WORKERS] * ldb;
+            p0[0] = base + (size_t)pre_s[0] * ldb, p0[1] = base + (size_t)pre_s[NUM_WORKERS] * ldb;
           } else {
-            row_ptrs(src0, bs, i0, rl, cofs, p0);
+            row_ptrs2(src0, bs, i0, r2, fcofs, p0);
           }
         }
         if constexpr (has_add1) {
           if (l == 0) {
-            const char* base = src_sample_base(L.add[1], bs) + 4 * cofs;
+            const char* base = src_sample_base(L.add[1], bs) + 4 * fcofs;
             const size_t ldb = 4 * (size_t)L.add[1].ld;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p1[k] = base + (size_t)pre_s[(4 + k) * NUM_WORKERS] * ldb;
+            p1[0] = base + (size_t)pre_s[2 * NUM_WORKERS] * ldb, p1[1] = base + (size_t)pre_s[3 * NUM_WORKERS] * ldb;
           } else {
-            row_ptrs(L.add[1], bs, i0, rl, cofs, p1);
+            row_ptrs2(L.add[1], bs, i0, r2, fcofs, p1);
           }
         }
       }
       const bool ld_on = !ABL3(ABL_LOADS);
-      uint32_t ld1 = 15u;  // which rows of addend 1 differ from the row before (the others repeat it and are not loaded)
-      if constexpr (has_add1) ld1 = 1u | (p1[1] != p1[0] ? 2u : 0u) | (p1[2] != p1[1] ? 4u : 0u) | (p1[3] != p1[2] ? 8u : 0u);
+      auto ld2 = [&](const char* const(&p)[2], int off, float(&o)[16]) { ld256(p[0] + off, o), ld256(p[1] + off, o + 8); };
       if constexpr (has0 && !has_ln) {
-        if (ld_on) ldfrag4(p0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
+        if (ld_on) ld2(p0, 0, pf0);  // (LayerNorm layers: after the statistics pass, which needs the registers)
       }
       if constexpr (has_add1) {
-        if (ld_on) ldfrag4_rep<0>(p1, pf1, ld1);
+        if (ld_on) ld2(p1, 0, pf1);
       }
       // targets of my rows (fused per-target sums): requested before the accumulator wait / the statistics pass
-      int dseg[4] = {0, 0, 0, 0}, dprev_q = 0;
+      int d0 = 0, d1 = 0, dprev_g = 0;
       if constexpr (has_seg) {
         const int32_t* sd = L.seg_dst + i0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dseg[k] = (re[k] < nvalid) ? __ldg(sd + re[k]) : -1 - k;
-        dprev_q = (lr == 0 && i0 + 32 * q > 0 && 32 * q < nvalid) ? __ldg(sd + 32 * q - 1) : -1 - 7;
+        d0 = (fr0 < nvalid) ? __ldg(sd + fr0) : -1;
+        d1 = (fr0 + 1 < nvalid) ? __ldg(sd + fr0 + 1) : -2;
+        dprev_g = (lr == 0 && i0 + frow > 0 && frow < nvalid) ? __ldg(sd + frow - 1) : -8;
       }
       if (!waited) {
         tr.ev(600 + l);
@@ -804,51 +748,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         tc_fence_after();
         tr.ev(610 + l);
       }
-      float rs[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};  // LayerNorm as v * rs[k] + sh[k] per row
+      float rs[2] = {1.f, 1.f}, sh[2] = {0.f, 0.f};  // LayerNorm as v * rs[m] + sh[m] per row
       if constexpr (has_ln) {
         if (!ABL3(ABL_LN)) {
-          float pv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          // Statistics (first pass over the accumulator): each thread reduces its 8 NP values of each of its 2 rows around a
+          // pivot (the row's first value), the partial (mean, M2) pairs are merged with Chan's formula over the 4 lanes and
+          // the 2 warps that share a row: one pass, no cancellation, one barrier.
+          float pv[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
           static_for<0, NP>([&](auto sc_) {
             constexpr int s = decltype(sc_)::value;
             float v[16];
-            tmem_ld_16x256b_x2(taddr + 64 * s, v);
-            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
+            tmem_ld_16x256b_x4(taddr + 64 * s, v);
             tmem_wait_ld();
-            const float4 b4 = lds128(bias_a + 256 * s);
+            const float4 bl = lds128(bias_a + 256 * s), bh = lds128(bias_a + 256 * s + 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col4(b4, i));
-            if constexpr (s == 0) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) pv[k] = v[8 * (k >> 1) + 2 * (k & 1)];
-            }
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col8(bl, bh, i));
+            if constexpr (s == 0) pv[0] = v[0], pv[1] = v[2];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int k = 2 * (i >> 3) + ((i >> 1) & 1);
-              const float d = v[i] - pv[k];
-              s1[k] += d;
-              s2[k] = fmaf(d, d, s2[k]);
+              const int m = (i >> 1) & 1;
+              const float d = v[i] - pv[m];
+              s1[m] += d;
+              s2[m] = fmaf(d, d, s2[m]);
             }
           });
           tr.ev(2001);
           if constexpr (has0) {
-            if (ld_on) ldfrag4(p0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
+            if (ld_on) ld2(p0, 0, pf0);  // residual rows of chunk 0: in flight during the merge below
           }
-          float mean[4], m2[4];
-          constexpr float inv_cnt = 1.0f / (4.0f * NP);
+          float mean[2], m2[2];
+          constexpr float inv_cnt = 1.0f / (8.0f * NP);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float a = s1[k] * inv_cnt;
-            mean[k] = pv[k] + a;
-            m2[k] = fmaxf(s2[k] - s1[k] * a, 0.f);
+          for (int m = 0; m < 2; ++m) {
+            const float a = s1[m] * inv_cnt;
+            mean[m] = pv[m] + a;
+            m2[m] = fmaxf(s2[m] - s1[m] * a, 0.f);
           }
 #pragma unroll
           for (int o = 1; o <= 2; o <<= 1) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float mb = __shfl_xor_sync(0xffffffffu, mean[k], o), qb = __shfl_xor_sync(0xffffffffu, m2[k], o);
-              const float d = mb - mean[k];
-              mean[k] = 0.5f * (mean[k] + mb);
-              m2[k] = (m2[k] + qb) + d * d * (o == 1 ? 2.0f * NP : 4.0f * NP);
+            for (int m = 0; m < 2; ++m) {
+              const float mb = __shfl_xor_sync(0xffffffffu, mean[m], o), qb = __shfl_xor_sync(0xffffffffu, m2[m], o);
+              const float d = mb - mean[m];
+              mean[m] = 0.5f * (mean[m] + mb);
+              m2[m] = (m2[m] + qb) + d * d * (o == 1 ? 4.0f * NP : 8.0f * NP);
             }
           }
           float* const ln_x = ln_base + (ln_gen & 1u) * (2 * WSPLIT * 128);
@@ -856,116 +799,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           ++ln_gen;
           if (lc == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ln_x[hq * 128 + rt[k]] = mean[k], ln_y[hq * 128 + rt[k]] = m2[k];
+            for (int m = 0; m < 2; ++m) ln_x[fc * 128 + frow + lr + 8 * m] = mean[m], ln_y[fc * 128 + frow + lr + 8 * m] = m2[m];
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this lane quadrant
+          asm volatile("bar.sync %0, 64;" ::"r"(fbar) : "memory");  // the two warps that share these rows
           tr.ev(2002);
-          constexpr float nw = 16.0f * NP;  // values per warp partial
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float n = 0.f, mu = 0.f, q2 = 0.f;
-#pragma unroll
-            for (int w = 0; w < WSPLIT; ++w) {  // same order in every thread of the row
-              const float mw = ln_x[w * 128 + rt[k]], qw = ln_y[w * 128 + rt[k]];
-              const float d = mw - mu, nt = n + nw;
-              mu += d * (nw / nt);
-              q2 += qw + d * d * (n * nw / nt);
-              n = nt;
-            }
+          for (int m = 0; m < 2; ++m) {  // same order in both warps of the row
+            const float ma = ln_x[frow + lr + 8 * m], mb = ln_x[128 + frow + lr + 8 * m];
+            const float qa = ln_y[frow + lr + 8 * m], qb = ln_y[128 + frow + lr + 8 * m];
+            const float d = mb - ma;
+            const float mu = ma + 0.5f * d;
+            const float q2 = (qa + qb) + d * d * (16.0f * NP);
             const float rstd = 1.0f / sqrtf(q2 * (1.0f / (64.0f * NP)) + 1e-5f);
-            rs[k] = rstd, sh[k] = -mu * rstd;
+            rs[m] = rstd, sh[m] = -mu * rstd;
           }
           tr.ev(2003);
         } else if constexpr (has0) {
-          if (ld_on) ldfrag4(p0, 0, pf0);
+          if (ld_on) ld2(p0, 0, pf0);
         }
       }
-      // output rows (fp32): row pointers + store predicates
-      char* po[4] = {nullptr, nullptr, nullptr, nullptr};
-      if constexpr (has_out) {
-        char* ob = reinterpret_cast<char*>(L.out + ((size_t)bs * rows + i0) * (size_t)L.ldo + cofs);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) po[k] = ob + (size_t)(uint32_t)re[k] * (4 * (size_t)L.ldo);
-      }
-      // fused per-target sums: which of my four consecutive rows start a new target, and who owns which piece
-      bool b1 = false, b2 = false, b3 = false, tail_st = false, head_st = false, inner_any = false;
-      float c1f = 0.f, c2f = 0.f, m1f = 1.f, m2f = 1.f, m3f = 1.f;
+      // output rows (fp32): my two rows are ldo apart
+      char* po = nullptr;
+      const size_t ostr = 4 * (size_t)L.ldo;
+      const bool st0 = fr0 < nvalid, st1 = fr0 + 1 < nvalid;
+      if constexpr (has_out) po = reinterpret_cast<char*>(L.out + ((size_t)bs * rows + i0 + fr0) * (size_t)L.ldo + fcofs);
+      // Fused per-target sums.  Rows are sorted by target, a target's rows are a run of at most 8 consecutive rows.  The 8 lane
+      // groups of a warp hold 16 consecutive rows, two per thread.  The thread in which a run STARTS owns it: it adds up its own
+      // rows of the run and the heads H (the rows before the first boundary) of the up to four following threads the run reaches
+      // into, left to right, and stores the sum.  A run that reaches the next 16-row group continues there; that group's first
+      // thread leaves the continuation in the carry buffer (gw_seg_carry_kernel adds it to the run's row afterwards).
+      bool bb = false, tail_st = false, head_st = false, one_st = false, one_any = false, deep = false;
+      float mbf = 1.f, c1f = 0.f, c2f = 0.f, c3f = 0.f, c4f = 0.f;
       char* tail_p = nullptr;
-      char* head_p = nullptr;
-      bool b0 = false;
+      char* carry_p = nullptr;
       if constexpr (has_seg) {
-        int dprev = __shfl_up_sync(0xffffffffu, dseg[3], 4);
-        if (lr == 0) dprev = dprev_q;
-        b0 = dseg[0] != dprev, b1 = dseg[1] != dseg[0], b2 = dseg[2] != dseg[1], b3 = dseg[3] != dseg[2];
-        const bool in123 = b1 || b2 || b3;
-        const uint32_t nb0 = __shfl_down_sync(0xffffffffu, (uint32_t)b0, 4), nin = __shfl_down_sync(0xffffffffu, (uint32_t)in123, 4);
-        const uint32_t nnb0 = __shfl_down_sync(0xffffffffu, (uint32_t)b0, 8);
-        const bool cont1 = lr < 7 && !nb0;                          // my last piece continues into the next thread's rows
-        const bool cont2 = cont1 && !nin && lr < 6 && !nnb0;        // ... and through all of them into the one after
-        c1f = cont1 ? 1.f : 0.f, c2f = cont2 ? 1.f : 0.f;
-        m1f = b1 ? 0.f : 1.f, m2f = b2 ? 0.f : 1.f, m3f = b3 ? 0.f : 1.f;
-        // the piece that ends with my row 3 is mine to store if it starts inside my rows, or if I hold the first rows of the
-        // quadrant (then it continues a segment of the previous quadrant / tile and goes to the carry buffer)
-        const bool starts_here = b0 || in123;
-        char* carry = reinterpret_cast<char*>(L.seg_carry + ((((size_t)bs * tiles_per_sample + (size_t)(i0 / TILE_M)) * 4 + q) * 256 + 64 * 0 + cofs));
-        if (starts_here) {
-          tail_st = dseg[3] >= 0;
-          tail_p = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)max(dseg[3], 0)) * (size_t)L.seg_ld + cofs);
+        int dprev = __shfl_up_sync(0xffffffffu, d1, 4);
+        if (lr == 0) dprev = dprev_g;
+        const bool ba = d0 != dprev;  // my first row starts a run
+        bb = d1 != d0;                // my second row starts a run
+        mbf = bb ? 0.f : 1.f;
+        const uint32_t fl = (ba ? 1u : 0u) | (bb ? 2u : 0u);
+        const uint32_t f1 = __shfl_down_sync(0xffffffffu, fl, 4), f2 = __shfl_down_sync(0xffffffffu, fl, 8);
+        const uint32_t f3 = __shfl_down_sync(0xffffffffu, fl, 12), f4 = __shfl_down_sync(0xffffffffu, fl, 16);
+        const bool c1 = lr < 7 && !(f1 & 1u);                      // my last run continues into the next thread's rows
+        const bool c2 = c1 && !(f1 & 2u) && lr < 6 && !(f2 & 1u);  // ... through both of them into the thread after
+        const bool c3 = c2 && !(f2 & 2u) && lr < 5 && !(f3 & 1u);
+        const bool c4 = c3 && !(f3 & 2u) && lr < 4 && !(f4 & 1u);
+        c1f = c1 ? 1.f : 0.f, c2f = c2 ? 1.f : 0.f, c3f = c3 ? 1.f : 0.f, c4f = c4 ? 1.f : 0.f;
+        deep = L.seg_maxdeg > 7;  // (a run of 8 rows can reach the fifth thread; 7 rows end in the fourth)
+        carry_p = reinterpret_cast<char*>(L.seg_carry + ((((size_t)bs * tiles_per_sample + (size_t)(i0 / TILE_M)) * 8 + (size_t)(2 * q + fh)) * 256 + fcofs));
+        // the run that ends with (or passes through) my second row: mine to store if it starts in my rows; the group's first
+        // thread stores the continuation of the previous group's run into the carry buffer
+        if (ba || bb) {
+          tail_st = d1 >= 0;
+          tail_p = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)max(d1, 0)) * (size_t)L.seg_ld + fcofs);
         } else if (lr == 0) {
-          tail_st = dseg[3] >= 0;
-          tail_p = carry;
+          tail_st = d1 >= 0;
+          tail_p = carry_p;
         }
-        // the quadrant's first thread also owns the piece BEFORE its first inner boundary when that piece continues the previous
-        // quadrant (the usual case: 32 is no multiple of the segment length): its sum is H below and goes to the carry buffer
-        head_st = lr == 0 && !b0 && in123 && dseg[0] >= 0;
-        head_p = carry;
-        // pieces that start AND end inside my four rows (segments shorter than four rows; never on the icosahedral graphs)
-        inner_any = __any_sync(0xffffffffu, (b1 && b0) || (b2 && (b0 || b1)) || (b3 && (b0 || b1 || b2)));
+        head_st = lr == 0 && !ba && bb && d0 >= 0;  // the previous group's run ends with my first row
+        one_st = ba && bb && d0 >= 0;               // my first row is a run of its own (a target with a single row)
+        one_any = __any_sync(0xffffffffu, one_st);
       }
       // The accumulator chunk s+1 is fetched from TMEM while chunk s is processed.
-      constexpr bool TM2 = true;  // (false: fetch each chunk when it is needed -- frees 16 registers; no measurable difference)
-      float vb[TM2 ? 2 : 1][16] = {};
+      float vb[2][16] = {};
       if constexpr (has_ln) tr.ev(2004);
-      if (TM2 && !ABL3(ABL_TMEM)) {
-        tmem_ld_16x256b_x2(taddr, vb[0]);
-        tmem_ld_16x256b_x2(taddr + (16u << 16), vb[0] + 8);
-      }
+      if (!ABL3(ABL_TMEM)) tmem_ld_16x256b_x4(taddr, vb[0]);
       static_for<0, NP>([&](auto sc_) {
         constexpr int s = decltype(sc_)::value;
-        float(&v)[16] = vb[TM2 ? (s & 1) : 0];
-        if constexpr (!TM2) {
-          if (!ABL3(ABL_TMEM)) {
-            tmem_ld_16x256b_x2(taddr + 64 * s, v);
-            tmem_ld_16x256b_x2(taddr + 64 * s + (16u << 16), v + 8);
-          }
-        }
+        float(&v)[16] = vb[s & 1];
         tmem_wait_ld_into(v);
         if constexpr (has_ln) tr.ev(2010 + s);
-        if constexpr (TM2 && s + 1 < NP) {
-          if (!ABL3(ABL_TMEM)) {
-            tmem_ld_16x256b_x2(taddr + 64 * (s + 1), vb[(s + 1) & 1]);
-            tmem_ld_16x256b_x2(taddr + 64 * (s + 1) + (16u << 16), vb[(s + 1) & 1] + 8);
-          }
-        }
-        if constexpr (s + 1 == NP) {  // my last read of this accumulator
+        if constexpr (s + 1 < NP) {
+          if (!ABL3(ABL_TMEM)) tmem_ld_16x256b_x4(taddr + 64 * (s + 1), vb[(s + 1) & 1]);
+        } else {  // my last read of this accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
         }
-        const float4 b4 = lds128(bias_a + 256 * s);
+        {
+          const float4 bl = lds128(bias_a + 256 * s), bh = lds128(bias_a + 256 * s + 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col4(b4, i));
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col8(bl, bh, i));
+        }
         if constexpr (has_add0) {
           if (ld_on) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf0[PX(i)];
           }
         }
         if constexpr (has_add1) {
           if (ld_on) {
-            fixrep4(pf1, ld1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += pf1[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf1[PX(i)];
           }
         }
         if constexpr (relu) {
@@ -973,73 +899,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if constexpr (has_ln) {
-          const float4 g4 = lds128(g_a + 256 * s), e4 = lds128(b_a + 256 * s);
+          const float4 gl = lds128(g_a + 256 * s), gh = lds128(g_a + 256 * s + 16);
+          const float4 el = lds128(b_a + 256 * s), eh = lds128(b_a + 256 * s + 16);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int k = 2 * (i >> 3) + ((i >> 1) & 1);
-            v[i] = fmaf(fmaf(v[i], rs[k], sh[k]), col4(g4, i), col4(e4, i));
+            const int m = (i >> 1) & 1;
+            v[i] = fmaf(fmaf(v[i], rs[m], sh[m]), col8(gl, gh, i), col8(el, eh, i));
           }
         }
         if constexpr (has_res) {
           if (ld_on) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += pf0[i];
+            for (int i = 0; i < 16; ++i) v[i] += pf0[PX(i)];
           }
         }
         if constexpr (has_ln) tr.ev(2020 + s);
         if constexpr (s + 1 < NP) {  // next chunk's global operands: in flight while this chunk is stored / converted
           if constexpr (has0) {
-            if (ld_on) ldfrag4(p0, 256 * (s + 1), pf0);
+            if (ld_on) ld2(p0, 256 * (s + 1), pf0);
           }
           if constexpr (has_add1) {
-            if (ld_on) ldfrag4_rep<256 * (s + 1)>(p1, pf1, ld1);
+            if (ld_on) ld2(p1, 256 * (s + 1), pf1);
           }
         }
         if constexpr (has_out) {
           if (!ABL3(ABL_STORES)) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (re[k] < nvalid) {
-                const int i = 8 * (k >> 1) + 2 * (k & 1);
-                *reinterpret_cast<float4*>(po[k] + 256 * s) = make_float4(v[i], v[i + 1], v[i + 4], v[i + 5]);
-              }
-            }
+            if (st0) st256(po + 256 * s, v[FR(0, 0)], v[FR(0, 1)], v[FR(0, 2)], v[FR(0, 3)], v[FR(0, 4)], v[FR(0, 5)], v[FR(0, 6)], v[FR(0, 7)]);
+            if (st1) st256(po + ostr + 256 * s, v[FR(1, 0)], v[FR(1, 1)], v[FR(1, 2)], v[FR(1, 3)], v[FR(1, 4)], v[FR(1, 5)], v[FR(1, 6)], v[FR(1, 7)]);
           }
         }
         if constexpr (has_ln) tr.ev(2030 + s);
         if constexpr (has_seg) {
-          // running sums over my four consecutive rows, restarted at every boundary; T = the piece ending with my row 3,
-          // H = the piece before my first inner boundary (all four rows if there is none): what earlier threads add to theirs
-          float T[4], H[4], r0[4], r1[4], r2[4];
+          float T[8], H[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int ci = 4 * (c >> 1) + (c & 1);
-            const float x0 = v[ci], x1 = v[ci + 2], x2 = v[ci + 8], x3 = v[ci + 10];
-            r0[c] = x0;
-            r1[c] = fmaf(m1f, r0[c], x1);  // m = 0 at a boundary (the running sum restarts), 1 inside a segment
-            r2[c] = fmaf(m2f, r1[c], x2);
-            T[c] = fmaf(m3f, r2[c], x3);
-            H[c] = b1 ? r0[c] : (b2 ? r1[c] : (b3 ? r2[c] : T[c]));
+          for (int t = 0; t < 8; ++t) {
+            const float xa = v[FR(0, t)], xb = v[FR(1, t)];
+            T[t] = fmaf(mbf, xa, xb);  // the run through my second row: both rows, or the second alone after a boundary
+            H[t] = bb ? xa : T[t];     // my rows before the first boundary: what the owner of the run that reaches me adds
           }
-          if (head_st && !ABL3(ABL_STORES)) *reinterpret_cast<float4*>(head_p + 256 * s) = make_float4(H[0], H[1], H[2], H[3]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float h1 = __shfl_down_sync(0xffffffffu, H[c], 4), h2 = __shfl_down_sync(0xffffffffu, H[c], 8);
-            T[c] = fmaf(c2f, h2, fmaf(c1f, h1, T[c]));
-          }
-          if (tail_st && !ABL3(ABL_STORES)) *reinterpret_cast<float4*>(tail_p + 256 * s) = make_float4(T[0], T[1], T[2], T[3]);
-          if (inner_any) {
-#pragma unroll
-            for (int j = 1; j <= 3; ++j) {
-              const bool bj = j == 1 ? b1 : (j == 2 ? b2 : b3);
-              const bool started = j == 1 ? b0 : (j == 2 ? (b0 || b1) : (b0 || b1 || b2));
-              if (bj && started && dseg[j - 1] >= 0) {
-                const float(&rr)[4] = j == 1 ? r0 : (j == 2 ? r1 : r2);
-                char* dp = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)dseg[j - 1]) * (size_t)L.seg_ld + cofs);
-                *reinterpret_cast<float4*>(dp + 256 * s) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-              }
+          const bool sts_on = !ABL3(ABL_STORES);
+          if (head_st && sts_on) st256(carry_p + 256 * s, H[0], H[1], H[2], H[3], H[4], H[5], H[6], H[7]);
+          if (one_any) {
+            if (one_st && sts_on) {
+              char* dp = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)d0) * (size_t)L.seg_ld + fcofs);
+              st256(dp + 256 * s, H[0], H[1], H[2], H[3], H[4], H[5], H[6], H[7]);
             }
           }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float h1 = __shfl_down_sync(0xffffffffu, H[t], 4), h2 = __shfl_down_sync(0xffffffffu, H[t], 8);
+            const float h3 = __shfl_down_sync(0xffffffffu, H[t], 12);
+            T[t] = fmaf(c3f, h3, fmaf(c2f, h2, fmaf(c1f, h1, T[t])));
+          }
+          if (deep) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) T[t] = fmaf(c4f, __shfl_down_sync(0xffffffffu, H[t], 16), T[t]);
+          }
+          if (tail_st && sts_on) st256(tail_p + 256 * s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7]);
         }
         if constexpr (feeds) {
           const uint32_t slot = (fi + s) % A_SLOTS;
@@ -1047,9 +963,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
                              // as a short predicated block the 16 multiplies would be issued (predicated off) in every chunk
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= osc;
-            if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
+            if (!ABL3(ABL_CONVERT)) store_operand_x4<SPLIT, false>(fsa + slot * A_SLOT_BYTES, v, amax);
           } else {
-            if (!ABL3(ABL_CONVERT)) store_operand_fast<SPLIT>(sa0 + slot * A_SLOT_BYTES, v, amax);
+            if (!ABL3(ABL_CONVERT)) store_operand_x4<SPLIT, false>(fsa + slot * A_SLOT_BYTES, v, amax);
           }
           publish(slot);
         }
@@ -1403,7 +1319,7 @@ static bool fits32(const RowSrc& s) {
   return span * (long long)s.ld * 4 + 4096 < (1ll << 32);
 }
 static bool src_fast(const RowSrc& s, int need) {
-  return simple_kind(s.kind) && s.width >= need && aligned16(s.base + s.col0) && !(s.ld & 3) && fits32(s);
+  return simple_kind(s.kind) && s.width >= need && aligned32(s.base + s.col0) && !(s.ld & 7) && fits32(s);  // 256-bit accesses
 }
 
 // Marks which parts of a chain take the lean full-width path (ch.fast) and the epilogue kind of every layer.
@@ -1437,8 +1353,9 @@ static void tc3_mark_lean(TcChain& ch) {
     for (int a = 0; a < 2; ++a)
       if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], L.N);
     if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, L.N);
-    if (L.out) ok = ok && aligned16(L.out) && !(L.ldo & 3) && L.out_cols >= L.N;
-    if (L.seg_dst) ok = ok && L.seg_out && L.seg_carry && aligned16(L.seg_out) && !(L.seg_ld & 3) && L.ln_g && L.N == 256;
+    if (L.out) ok = ok && aligned32(L.out) && !(L.ldo & 7) && L.out_cols >= L.N;
+    if (L.seg_dst) ok = ok && L.seg_out && L.seg_carry && aligned32(L.seg_out) && aligned32(L.seg_carry) && !(L.seg_ld & 7) && L.ln_g && L.N == 256;
+    ok = ok && L.Wp32 != nullptr;
     const int f = (L.add[0].kind != SRC_NONE ? F_ADD0 : 0) | (L.add[1].kind != SRC_NONE ? F_ADD1 : 0) | (L.relu ? F_RELU : 0) |
                   (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0) |
                   (L.seg_dst ? F_SEG : 0);
@@ -1507,6 +1424,8 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   // (mode 2, per-part selection inside one kernel, measured slower than the general path: both paths' live state spills)
   int mode = ch.fast == all ? 1 : 0;
   if (ch.out_mode != 0) mode = 0;  // the multi-GPU boundary stores live in the general path's store tiers
+  if (mode == 1)
+    for (int l = 0; l < ch.n_layers; ++l) ch.layer[l].Wp = ch.layer[l].Wp32;  // the lean path's feature order (perm32)
   if (mode == 0)
     for (int l = 0; l < ch.n_layers; ++l)
       if (ch.layer[l].seg_dst) return cudaErrorInvalidValue;  // the fused per-target sum exists on the lean path only
