@@ -755,11 +755,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           // pivot (the row's first value), the partial (mean, M2) pairs are merged with Chan's formula over the 4 lanes and
           // the 2 warps that share a row: one pass, no cancellation, one barrier.
           float pv[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+          float sv[2][16];  // chunk s+1 is fetched from TMEM while chunk s is accumulated
+          tmem_ld_16x256b_x4(taddr, sv[0]);
           static_for<0, NP>([&](auto sc_) {
             constexpr int s = decltype(sc_)::value;
-            float v[16];
-            tmem_ld_16x256b_x4(taddr + 64 * s, v);
-            tmem_wait_ld();
+            float(&v)[16] = sv[s & 1];
+            tmem_wait_ld_into(v);
+            if constexpr (s + 1 < NP) tmem_ld_16x256b_x4(taddr + 64 * (s + 1), sv[(s + 1) & 1]);
             const float4 bl = lds128(bias_a + 256 * s), bh = lds128(bias_a + 256 * s + 16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col8(bl, bh, i));
@@ -824,12 +826,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       const bool st0 = fr0 < nvalid, st1 = fr0 + 1 < nvalid;
       if constexpr (has_out) po = reinterpret_cast<char*>(L.out + ((size_t)bs * rows + i0 + fr0) * (size_t)L.ldo + fcofs);
       // Fused per-target sums.  Rows are sorted by target, a target's rows are a run of at most 8 consecutive rows.  The 8 lane
-      // groups of a warp hold 16 consecutive rows, two per thread.  The thread in which a run STARTS owns it: it adds up its own
-      // rows of the run and the heads H (the rows before the first boundary) of the up to four following threads the run reaches
-      // into, left to right, and stores the sum.  A run that reaches the next 16-row group continues there; that group's first
-      // thread leaves the continuation in the carry buffer (gw_seg_carry_kernel adds it to the run's row afterwards).
+      // groups of a warp hold 16 consecutive rows, two per thread.  The thread in which a run STARTS owns it: it adds to its own
+      // rows of the run the heads H (the rows before the first boundary) of the following threads the run reaches into, and
+      // stores the sum.  The heads are chained by doubling: G1(t) = H(t) + k(t) H(t+1) where k(t) = "the run passes through
+      // thread t into t+1"; the owner takes H(t+1) and G1(t+2) (two shuffles per value reach four threads = 7 rows; a third,
+      // G2(t+4), reaches the fifth thread an 8-row run can touch).  A run that reaches the next 16-row group continues there; that
+      // group's first thread leaves the continuation in the carry buffer (gw_seg_carry_kernel adds it to the run's row afterwards).
       bool bb = false, tail_st = false, head_st = false, one_st = false, one_any = false, deep = false;
-      float mbf = 1.f, c1f = 0.f, c2f = 0.f, c3f = 0.f, c4f = 0.f;
+      float mbf = 1.f, c1f = 0.f, e2f = 0.f, e4f = 0.f, kf = 0.f, k1f = 0.f;
       char* tail_p = nullptr;
       char* carry_p = nullptr;
       if constexpr (has_seg) {
@@ -838,14 +842,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         const bool ba = d0 != dprev;  // my first row starts a run
         bb = d1 != d0;                // my second row starts a run
         mbf = bb ? 0.f : 1.f;
-        const uint32_t fl = (ba ? 1u : 0u) | (bb ? 2u : 0u);
-        const uint32_t f1 = __shfl_down_sync(0xffffffffu, fl, 4), f2 = __shfl_down_sync(0xffffffffu, fl, 8);
-        const uint32_t f3 = __shfl_down_sync(0xffffffffu, fl, 12), f4 = __shfl_down_sync(0xffffffffu, fl, 16);
-        const bool c1 = lr < 7 && !(f1 & 1u);                      // my last run continues into the next thread's rows
-        const bool c2 = c1 && !(f1 & 2u) && lr < 6 && !(f2 & 1u);  // ... through both of them into the thread after
-        const bool c3 = c2 && !(f2 & 2u) && lr < 5 && !(f3 & 1u);
-        const bool c4 = c3 && !(f3 & 2u) && lr < 4 && !(f4 & 1u);
-        c1f = c1 ? 1.f : 0.f, c2f = c2 ? 1.f : 0.f, c3f = c3 ? 1.f : 0.f, c4f = c4 ? 1.f : 0.f;
+        const uint32_t nba = __shfl_down_sync(0xffffffffu, (uint32_t)ba, 4);
+        const bool c1 = lr < 7 && !nba;  // my last run continues into the next thread's rows
+        const bool k = c1 && !bb;        // ... and it entered my rows from the left or at my first row: it passes THROUGH me
+        const uint32_t k1 = __shfl_down_sync(0xffffffffu, (uint32_t)k, 4), k2 = __shfl_down_sync(0xffffffffu, (uint32_t)k, 8);
+        const uint32_t k3 = __shfl_down_sync(0xffffffffu, (uint32_t)k, 12);
+        const bool e2 = c1 && k1;         // (k(t+1) implies lane group t+2 exists)
+        const bool e4 = e2 && k2 && k3;
+        c1f = c1 ? 1.f : 0.f, e2f = e2 ? 1.f : 0.f, e4f = e4 ? 1.f : 0.f, kf = k ? 1.f : 0.f, k1f = (k && k1) ? 1.f : 0.f;
         deep = L.seg_maxdeg > 7;  // (a run of 8 rows can reach the fifth thread; 7 rows end in the fourth)
         carry_p = reinterpret_cast<char*>(L.seg_carry + ((((size_t)bs * tiles_per_sample + (size_t)(i0 / TILE_M)) * 8 + (size_t)(2 * q + fh)) * 256 + fcofs));
         // the run that ends with (or passes through) my second row: mine to store if it starts in my rows; the group's first
@@ -947,13 +951,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           }
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const float h1 = __shfl_down_sync(0xffffffffu, H[t], 4), h2 = __shfl_down_sync(0xffffffffu, H[t], 8);
-            const float h3 = __shfl_down_sync(0xffffffffu, H[t], 12);
-            T[t] = fmaf(c3f, h3, fmaf(c2f, h2, fmaf(c1f, h1, T[t])));
+            const float h1 = __shfl_down_sync(0xffffffffu, H[t], 4);
+            T[t] = fmaf(c1f, h1, T[t]);
+            H[t] = fmaf(kf, h1, H[t]);  // G1
           }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) T[t] = fmaf(e2f, __shfl_down_sync(0xffffffffu, H[t], 8), T[t]);
           if (deep) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) T[t] = fmaf(c4f, __shfl_down_sync(0xffffffffu, H[t], 16), T[t]);
+            for (int t = 0; t < 8; ++t) {
+              const float g2 = fmaf(k1f, __shfl_down_sync(0xffffffffu, H[t], 8), H[t]);  // G2
+              T[t] = fmaf(e4f, __shfl_down_sync(0xffffffffu, g2, 16), T[t]);
+            }
           }
           if (tail_st && sts_on) st256(tail_p + 256 * s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7]);
         }

@@ -360,6 +360,35 @@ def test_processor_rereads_its_graph_every_call(precision):
         assert float((out - ref).abs().max()) < TOL, trial
 
 
+@pytest.mark.parametrize("maxdeg", [7, 8])
+def test_fused_target_sums_cover_every_run_shape(maxdeg):
+    """The per-target sums fused into the edge chain's last layer (gw_tc3.cu, lean path): targets with 1 .. maxdeg incoming edges
+    in random order -- runs of a single row, runs that start on either row of a thread, runs that cross 16-row group and tile
+    boundaries, the 8-row runs that reach a fifth thread -- against the oracle (Processor.forward, processor.py:83)."""
+    from graph_weather_b200 import Processor
+    from oracle import restate, weights
+
+    sd_all = weights.make_state_dict(weights.forecaster_shapes(), 17)
+    sd = {k[len("processor."):]: v for k, v in sd_all.items() if k.startswith("processor.")}
+    proc = Processor(precision="fp32").cuda()
+    proc.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(5)
+    n = 700
+    deg = torch.randint(1, maxdeg + 1, (n,), generator=gen)
+    deg[:8] = torch.tensor([1, 1, maxdeg, 1, maxdeg, maxdeg, 2, 1])
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    e = int(dst.numel())
+    perm = torch.randperm(e, generator=gen)  # the caller's edge order is arbitrary
+    dst = dst[perm]
+    src = torch.randint(0, n, (e,), generator=gen)
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, 256, generator=gen)
+    ea = torch.randn(e, 256, generator=gen)
+    out = proc(x.cuda(), ei.cuda(), ea.cuda()).cpu()
+    ref = restate.processor_forward(sd_all, x, ei, ea, 9)
+    assert float((out - ref).abs().max()) < TOL
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_assimilator_rebuilds_the_observation_graph(precision):
     """GraphWeatherAssimilator builds its input graph from lat_lon_heights on every call (assimilator_encoder.py:118): two
