@@ -416,6 +416,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
     // ===================================== weight producer =========================================================
     if (lane == 0) {
       uint32_t bi = 0;
+      Tracer tr;
+      tr.init(ch.trace, 0, true);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < ch.n_layers; ++l) {
           const TcLayer& L = ch.layer[l];
@@ -426,6 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             for (int part = 0; part < parts; ++part, ++bi) {
               const uint32_t stage = bi % B_STAGES, n = bi / B_STAGES;
               mbar_wait(bar_empty_b + 8 * stage, (n & 1) ^ 1, ch.status);
+              tr.ev(50 + 10 * l + 2 * kc + part);
               if (ABL3(ABL_WEIGHTS)) {
                 mbar_arrive(bar_full_b + 8 * stage);
                 continue;
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
               mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
               tc_fence_after();
+              tr.ev(210 + kc);
               const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
               if (!ABL3(ABL_MMA)) {
 #pragma unroll
@@ -482,8 +486,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             }
             if (split) {  // lo weight panel: A_hi.B_lo
               const uint32_t stage = bi % B_STAGES, nb = bi / B_STAGES;
+              tr.ev(215 + kc);
               mbar_wait(bar_full_b + 8 * stage, nb & 1, ch.status);
               tc_fence_after();
+              tr.ev(220 + kc);
               const uint32_t b = sbase + OFF_B + stage * B_STAGE_BYTES;
               if (!ABL3(ABL_MMA)) {
 #pragma unroll
