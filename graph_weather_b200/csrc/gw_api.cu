@@ -419,7 +419,10 @@ static int bind_all(gw_plan* p) {
     GW_TRY(bind_mlp(p, "decoder.edge_encoder", 2, He, De, 2, true, &p->dec_edge_enc));  // 2 hidden layers hard-coded: assimilator_decoder.py:109
     GW_TRY(bind_mlp(p, "decoder.graph_processor.blocks.0.edge_model.edge_mlp", 2 * Dn + De, He, De, Le, true, &p->dec_blk_edge));
     GW_TRY(bind_mlp(p, "decoder.graph_processor.blocks.0.node_model.node_mlp", Dn + De, Hn, Dn, Ln, true, &p->dec_blk_node));
-    GW_TRY(bind_mlp(p, "decoder.node_decoder", Dn, d.hidden_dec, d.out_dim, d.hidden_layers_dec, false, &p->dec_node_dec));
+    // (no norm in the forecaster / assimilator decoders, decoder.py / assimilator_decoder.py; the regional forecaster builds its
+    // node decoder WITH the configured norm, regional_forecast.py:224-231: bound when its parameters are present)
+    const bool nd_norm = has(("decoder.node_decoder.model." + std::to_string(2 * d.hidden_layers_dec + 1) + ".weight").c_str());
+    GW_TRY(bind_mlp(p, "decoder.node_decoder", Dn, d.hidden_dec, d.out_dim, d.hidden_layers_dec, nd_norm, &p->dec_node_dec));
     p->w_dec = true;
   }
   GW_CHECK(p->w_enc || p->w_proc || p->w_dec, "no encoder./processor./decoder. parameter group found in the table");
@@ -466,7 +469,7 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
     want(p->dec_blk_node.W[0] + Dn, p->dec_blk_node.in[0], De, p->dec_blk_node.out[0], &p->tc_dec_node.w0);  // agg half
     tail(p->dec_blk_node, p->tc_dec_node);
     const Mlp& md = p->dec_node_dec;
-    p->tc_dec_out_ok = md.L == 2 && (d.hidden_dec % 64 == 0) && d.hidden_dec <= 256 && d.out_dim <= 256;
+    p->tc_dec_out_ok = md.L == 2 && (d.hidden_dec % 64 == 0) && d.hidden_dec <= 256 && d.out_dim <= 256 && !md.ln_g;  // (a LayerNorm over out_dim columns: CUDA cores)
     if (p->tc_dec_out_ok) {
       want(md.W[0], md.in[0], md.in[0], md.out[0], &p->tc_dec_out.w0);
       tail(md, p->tc_dec_out);
@@ -996,7 +999,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
         GemmOp fo = first_op(No, 1, src_stream(xg + (size_t)b * No * Dn, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
         RowSrc res;
         if (start && d.residual_dim > 0) res = src_stream(start + (size_t)(s0 + b) * No * start_ld, start_ld, d.out_dim, No);
-        GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)(s0 + b) * No * out_ld, out_ld, st));
+        GW_TRY(run_mlp(p, m, fo, false, m.ln_g != nullptr, res, out + (size_t)(s0 + b) * No * out_ld, out_ld, st));
       }
       continue;
     }
@@ -1028,7 +1031,7 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
       GemmOp fo = first_op(No, cb, src_stream(xg, Dn, Dn, No), none, m.W[0], m.in[0], m.in[0], m.b[0]);
       RowSrc res;
       if (start && d.residual_dim > 0) res = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
-      GW_TRY(run_mlp(p, m, fo, false, false, res, out + (size_t)s0 * No * out_ld, out_ld, st));
+      GW_TRY(run_mlp(p, m, fo, false, m.ln_g != nullptr, res, out + (size_t)s0 * No * out_ld, out_ld, st));
     }
   }
   return 0;

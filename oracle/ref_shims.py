@@ -147,7 +147,13 @@ def load_reference():
         gcp.__path__ = [os.path.join(base, "models", "graphcast")]
         sys.modules["graph_weather.models.graphcast"] = gcp
     gc = importlib.import_module("graph_weather.models.graphcast.model")
+    dgb = importlib.import_module("graph_weather.models.layers.dynamic_graph_builder")  # needs graph_weather.utils (plain python)
+    reg = importlib.import_module("graph_weather.models.regional_forecast")
     ns = types.SimpleNamespace(
+        DynamicGraphBuilder=dgb.DynamicGraphBuilder,
+        RegionalForecaster=reg.RegionalForecaster,
+        RegionalForecasterConfig=reg.RegionalForecasterConfig,
+        BoundaryNudgingLayer=reg.BoundaryNudgingLayer,
         MLP=gnb.MLP,
         GraphProcessor=gnb.GraphProcessor,
         Encoder=enc.Encoder,

@@ -202,6 +202,64 @@ def forecaster_forward(sd, g, features, feature_dim=78, num_blocks=9, hl_node=2,
         return out + features[..., :feature_dim]
 
 
+def regional_graphs(lat_lons, resolution=2):
+    """DynamicGraphBuilder.__call__ (dynamic_graph_builder.py:31-66, :100-155), loop for loop: the encoder graph (one edge per
+    coordinate -> its cell, cells numbered over the sorted unique cells), the latent graph among those cells, and the cells' ranks
+    in the global sorted cell list (rows of the embedding table)."""
+    lat_lons = [tuple(map(float, p)) for p in lat_lons]
+    all_h3 = sorted(h3.uncompact_cells(h3.get_res0_cells(), resolution))
+    global_map = {c: i for i, c in enumerate(all_h3)}
+    cells = [h3.latlng_to_cell(lat, lon, resolution) for lat, lon in lat_lons]
+    unique_cells = sorted(set(cells))
+    local = {c: i for i, c in enumerate(unique_cells)}
+    n = len(lat_lons)
+    src, dst, attr = [], [], []
+    for i, (coord, cell) in enumerate(zip(lat_lons, cells)):
+        d = h3.great_circle_distance(coord, h3.cell_to_latlng(cell), unit="rads")
+        src.append(i), dst.append(n + local[cell]), attr.append([np.sin(d), np.cos(d)])
+    enc_ei = torch.tensor([src, dst], dtype=torch.long)
+    enc_ea = torch.tensor(attr, dtype=torch.float)
+    ls, ld, la = [], [], []
+    for cell in unique_cells:
+        for h in h3.grid_disk(cell, 1):
+            if h in local:
+                d = h3.great_circle_distance(h3.cell_to_latlng(cell), h3.cell_to_latlng(h), unit="rads")
+                ls.append(local[cell]), ld.append(local[h]), la.append([np.sin(d), np.cos(d)])
+    return dict(enc_edge_index=enc_ei, enc_edge_attr=enc_ea, lat_edge_index=torch.tensor([ls, ld], dtype=torch.long),
+                lat_edge_attr=torch.tensor(la, dtype=torch.float), h3_indices=[global_map[c] for c in unique_cells], num_obs=n)  # fmt: skip
+
+
+def regional_forward(sd, g, features, output_dim=78, num_blocks=9, hl_node=2, hl_edge=2, hl_dec=2, global_context=None, lat_lons=None):
+    """RegionalForecaster.forward (regional_forecast.py:233-298), one sample at a time as there; sd has the reference's keys."""
+    with torch.no_grad():
+        n = g["num_obs"]
+        regional_h3 = sd["h3_embeddings"][torch.tensor(g["h3_indices"], dtype=torch.long)]
+        enc_ea = mlp(sd, "edge_encoder", g["enc_edge_attr"], hl_edge)
+        lat_ea = mlp(sd, "latent_edge_encoder", g["lat_edge_attr"], hl_edge)
+        dec_ei = g["enc_edge_index"].flip(0)
+        dec_ea = mlp(sd, "decoder_edge_encoder", g["enc_edge_attr"], hl_edge)
+        outs = []
+        for i in range(features.shape[0]):
+            nodes = mlp(sd, "node_encoder", torch.cat([features[i], regional_h3], dim=0), hl_node)
+            nodes, _ = graph_processor(sd, "encoder_gnn", nodes, g["enc_edge_index"], enc_ea.clone(), 1, hl_node, hl_edge)
+            x = processor_forward(sd, nodes[n:], g["lat_edge_index"], lat_ea.clone(), num_blocks, "processor", hl_node, hl_edge)
+            dec_nodes = torch.cat([torch.zeros(n, x.shape[-1]), x], dim=0)
+            dec_nodes, _ = graph_processor(sd, "decoder_gnn", dec_nodes, dec_ei, dec_ea.clone(), 1, hl_node, hl_edge)
+            outs.append(mlp(sd, "node_decoder", dec_nodes[:n], hl_dec, norm=True))  # built WITH the configured norm (:224-231)
+        out = torch.stack(outs, dim=0) + features[..., :output_dim]
+        if global_context is not None:  # BoundaryNudgingLayer.forward (:68-90) with the relaxation prior of :92-130
+            lats = torch.tensor([ll[0] for ll in lat_lons], dtype=torch.float32) * (np.pi / 180.0)
+            lons = torch.tensor([ll[1] for ll in lat_lons], dtype=torch.float32) * (np.pi / 180.0)
+            a = torch.sin((lats - lats.mean()) / 2) ** 2 + torch.cos(lats) * torch.cos(lats.mean()) * torch.sin((lons - lons.mean()) / 2) ** 2
+            dist = 2 * torch.asin(torch.sqrt(torch.clamp(a, 0.0, 1.0)))
+            prior = (dist / dist.max() if dist.max() > 0 else torch.zeros_like(dist)).unsqueeze(-1).unsqueeze(0).expand(out.shape[0], -1, -1)
+            h = torch.cat([out, global_context, prior], dim=-1)
+            corr = mlp(sd, "nudging.blend_mlp", h, 1, norm=False)
+            alpha = torch.clamp(prior + corr, 0.0, 1.0)
+            out = (1 - alpha) * out + alpha * global_context
+        return out
+
+
 def assimilator_forward(sd, g_static, features, lat_lon_heights, resolution=2, num_blocks=9, hl_node=2, hl_edge=2, hl_dec=2):
     """analysis.py:147-149 with assimilator_encoder.py:118-168 (input graph rebuilt per call; h3_nodes is a plain
     zero tensor, not a parameter, assimilator_encoder.py:80). g_static: base_h3_grid, lat_*, dec_*, num_latlons(out), num_h3."""

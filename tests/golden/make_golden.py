@@ -176,6 +176,37 @@ def run_constraints(R, name="forecaster_constraints_10deg_b2"):
         hr=hr.numpy(), lr=lr.numpy(), **layer_out)  # fmt: skip
 
 
+def regional_region():
+    """A 0.5-degree box over western Europe plus a few scattered points (one near a pentagon): the movable domain of the test."""
+    ll = [(38.0 + 0.5 * i, -12.0 + 0.5 * j) for i in range(40) for j in range(61)]
+    ll += [(10.4, -54.2), (10.9, -53.7), (58.1, 10.9), (58.4, 11.3), (63.0, -20.0)]
+    return ll
+
+
+def run_regional(R, name="regional_europe_b2"):
+    """RegionalForecaster (regional_forecast.py) with boundary nudging, default sizes, seeded weights: outputs without and with a
+    global context; the state_dict key / shape contract and the graph sizes travel with the fixture."""
+    lat_lons = regional_region()
+    cfg = R.RegionalForecasterConfig(enable_nudging=True)
+    model = R.RegionalForecaster(cfg)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = weights.make_state_dict(shapes, 21)
+    model.load_state_dict(sd)
+    x = weights.make_features(2, len(lat_lons), 102, 21)
+    gc = weights.make_features(2, len(lat_lons), 78, 22)
+    with torch.no_grad():
+        out = model(x, lat_lons)
+        out_n = model(x, lat_lons, global_context=gc)
+    enc, _dec, lat, h3_idx = model.graph_builder(lat_lons)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), config=json.dumps(dict(seed=21, batch=2, keys=list(shapes.keys()), shapes=[list(v) for v in shapes.values()])),
+        lat_lons=np.array(lat_lons, dtype=np.float64), out=out.numpy(), out_nudged=out_n.numpy(), h3_indices=np.array(h3_idx, dtype=np.int64),
+        enc_edge_index=enc.edge_index.numpy().astype(np.int32), lat_edge_index=lat.edge_index.numpy().astype(np.int32),
+        lat_edge_attr=lat.edge_attr.numpy())  # fmt: skip
+    print(name, "out", tuple(out.shape), "cells", len(h3_idx), "latent edges", lat.edge_index.shape[1], "mean|out|", float(out.abs().mean()),
+          "mean|nudged - out|", float((out_n - out).abs().mean()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     R = ref_shims.load_reference()
@@ -191,3 +222,5 @@ if __name__ == "__main__":
         run_loss()
     if not only or "constraints" in only:
         run_constraints(R)
+    if not only or "regional" in only:
+        run_regional(R)
