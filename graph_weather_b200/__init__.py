@@ -5,6 +5,7 @@ Public names mirror graph_weather/__init__.py:3-9 and graph_weather/models/__ini
 
 from .constraint import PhysicalConstraintLayer  # noqa: F401
 from .losses import NormalizedMSELoss  # noqa: F401
+from .dynamic_graph_builder import DynamicGraphBuilder  # noqa: F401
 from .models import (  # noqa: F401
     AssimilatorDecoder,
     AssimilatorEncoder,
@@ -18,9 +19,11 @@ from .models import (  # noqa: F401
     GraphWeatherForecasterConfig,
     Processor,
 )
+from .regional import BoundaryNudgingLayer, RegionalForecaster, RegionalForecasterConfig  # noqa: F401
 
 __all__ = [
     "GraphWeatherForecaster", "GraphWeatherForecasterConfig", "GraphWeatherAssimilator", "GraphWeatherAssimilatorConfig",
     "GraphCast", "GraphCastConfig", "Encoder", "Processor", "Decoder", "AssimilatorEncoder", "AssimilatorDecoder",
-    "NormalizedMSELoss", "PhysicalConstraintLayer",
+    "NormalizedMSELoss", "PhysicalConstraintLayer", "DynamicGraphBuilder", "RegionalForecaster", "RegionalForecasterConfig",
+    "BoundaryNudgingLayer",
 ]  # fmt: skip

@@ -615,17 +615,19 @@ cudaError_t launch_csr_expand(const int32_t* ptr, int n, int32_t* dst, int* stat
   return cudaGetLastError();
 }
 // A segment cut by a 16-row group boundary of the chain kernel's tiles (the rows one worker warp reduces, gw_tc3.cu) left the
-// sum of its later rows in `carry` ([batch][tiles][8][256]); add it to the segment's row of out.  One 64-thread CTA per
-// (boundary, sample); fixed order.
-__global__ void __launch_bounds__(64) gw_seg_carry_kernel(const float* __restrict__ carry, const int32_t* __restrict__ seg_dst, int rows,
-                                                          int tiles, int seg_rows, float* __restrict__ out, int ldo) {
-  const int bg = blockIdx.x, b = blockIdx.y;  // boundary = tile * 8 + group
+// sum of its later rows in `carry` ([batch][tiles][8][256]); add it to the segment's row of out.  64 threads per boundary, four
+// boundaries per CTA (a quarter of a million one-boundary CTAs cost more in launch overhead than in work); fixed order.
+__global__ void __launch_bounds__(256) gw_seg_carry_kernel(const float* __restrict__ carry, const int32_t* __restrict__ seg_dst, int rows,
+                                                           int tiles, int seg_rows, float* __restrict__ out, int ldo) {
+  const int bg = blockIdx.x * 4 + (threadIdx.x >> 6), b = blockIdx.y;  // boundary = tile * 8 + group
+  const int t = threadIdx.x & 63;
+  if (bg >= tiles * 8) return;
   const int r = (bg >> 3) * 128 + (bg & 7) * 16;
   if (r <= 0 || r >= rows) return;
   const int d = __ldg(seg_dst + r);
   if (__ldg(seg_dst + r - 1) != d) return;  // the group starts a new segment: nothing was carried
-  const float4 c = __ldg(reinterpret_cast<const float4*>(carry + ((size_t)b * tiles * 8 + bg) * 256 + threadIdx.x * 4));
-  float4* o = reinterpret_cast<float4*>(out + ((size_t)b * seg_rows + d) * (size_t)ldo + threadIdx.x * 4);
+  const float4 c = __ldg(reinterpret_cast<const float4*>(carry + ((size_t)b * tiles * 8 + bg) * 256 + t * 4));
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)b * seg_rows + d) * (size_t)ldo + t * 4);
   float4 v = *o;
   v.x += c.x, v.y += c.y, v.z += c.z, v.w += c.w;
   *o = v;
@@ -634,7 +636,7 @@ cudaError_t launch_seg_carry(const float* carry, const int32_t* seg_dst, int row
                              cudaStream_t stream) {
   if (rows <= 0 || batch <= 0) return cudaSuccess;
   const int tiles = (rows + 127) / 128;
-  gw_seg_carry_kernel<<<dim3(tiles * 8, batch), 64, 0, stream>>>(carry, seg_dst, rows, tiles, seg_rows, out, ldo);
+  gw_seg_carry_kernel<<<dim3(tiles * 2, batch), 256, 0, stream>>>(carry, seg_dst, rows, tiles, seg_rows, out, ldo);
   count_launch();
   return cudaGetLastError();
 }
