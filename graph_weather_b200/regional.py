@@ -211,6 +211,10 @@ class RegionalForecaster(nn.Module):
             raise ValueError(f"features has {N} rows per sample but lat_lons has {len(lat_lons)} coordinates")
         if features.shape[-1] < self.output_dim:
             raise RuntimeError(f"features needs at least output_dim ({self.output_dim}) channels for the residual add (:288)")
+        if torch.is_grad_enabled() and self.training and (features.requires_grad or any(q.requires_grad for q in self.parameters())):
+            # (the forecaster's backward, csrc/gw_train.inl, is not wired to this module: fail instead of returning a tensor
+            # that silently carries no graph)
+            raise NotImplementedError("RegionalForecaster: the training step is not built; call under torch.no_grad() or in eval() mode")
         region, eng = self._region(lat_lons)
         named = self._named(region, features.device)
         plan = eng.ensure(features.device, B, named)
