@@ -118,6 +118,8 @@ struct gw_plan {
   DevBuf<float> zeros_h3;
   // weight constants
   DevBuf<float> e_enc, xm0, C1_enc, e_lat, e_dec, E1_dec, tmpP;
+  DevBuf<float> S_dec;  // [n_out, De] tensor-core plans: per lat/lon point, the sum of e_dec over the point's decoder edges (the constant residual of
+                        // the decoder's edge MLP, summed once per weight set instead of being read per edge in every forward)
   // scratch
   // scratch.  chunk = samples processed per pass through the encoder / decoder stages.
   int chunk = 1;
@@ -208,7 +210,7 @@ static RowSrc src_gather_bcast_relu(const float* base, int ld, int width, const 
 
 // magnitude-bound slots (gw_plan::bounds)
 enum BoundSlot { SL_FEAT = 0, SL_XIN, SL_XOUT, SL_X0, SL_X1, SL_E0, SL_E1, SL_EIN, SL_P, SL_AGG_MESH, SL_AGG_GRID, SL_ROWS_N, SL_ROWS_E,
-                 SL_EENC, SL_C1ENC, SL_XM0, SL_ELAT, SL_EDEC, SL_E1DEC, SL_COUNT };
+                 SL_EENC, SL_C1ENC, SL_XM0, SL_ELAT, SL_EDEC, SL_E1DEC, SL_SDEC, SL_COUNT };
 static float* sl(gw_plan* p, int i) { return p->bounds.p + i; }
 static RowSrc bounded(RowSrc s, const float* b, float mul = 1.f) {
   s.bound = b, s.bound_mul = mul;
@@ -602,6 +604,8 @@ static int precompute_constants(gw_plan* p, cudaStream_t st) {
     c.W = e.W[0] + 2 * Dn, c.K = De, c.ldw = e.in[0], c.N = He, c.bias = e.b[0];
     c.out = p->E1_dec.p, c.ldo = He;
     GW_TRY(run_op(p, c, st));
+    if (is_tc(p) && p->S_dec.p)  // sum_e (e_dec[e] + LN(..)) = S_dec[point] + sum_e LN(..): graph_net_block.py:133,188 reassociated
+      GW_CUDA(launch_segsum(p->e_dec.p, De, De, p->dec_ptr.p, nullptr, d.n_dec_edges, d.n_out, 1, p->S_dec.p, De, st));
   }
   if (p->w_enc && p->have_enc) GW_TRY(precompute_encoder_constants(p, st));
   if (is_tc(p)) {  // magnitude bounds of the constant tensors the chains read (operand range, gw_tc3.cu)
@@ -610,6 +614,7 @@ static int precompute_constants(gw_plan* p, cudaStream_t st) {
     if (p->w_dec && p->have_dec) {
       GW_TRY(raw_bound(p, SL_EDEC, p->e_dec.p, (long long)d.n_dec_edges * De, st));
       GW_TRY(raw_bound(p, SL_E1DEC, p->E1_dec.p, (long long)d.n_dec_edges * He, st));
+      if (p->S_dec.p) GW_TRY(raw_bound(p, SL_SDEC, p->S_dec.p, (long long)d.n_out * De, st));
     }
   }
   return 0;
@@ -923,9 +928,11 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
         ch.K0 = He;
         ch.layer[0] = tc_layer(p->tc_dec_edge.w1, &me, 1, true, true);
         ch.layer[1] = tc_layer(p->tc_dec_edge.w2, &me, 2, false, false);
-        tc_ln(ch.layer[1], me, bounded(src_bcast(p->e_dec.p, De, De), sl(p, SL_EDEC)));
+        // (fused sums: the constant residual e_dec is not read per edge -- its per-point sum S_dec joins each finished sum)
+        tc_ln(ch.layer[1], me, fuse && p->S_dec.p ? none : bounded(src_bcast(p->e_dec.p, De, De), sl(p, SL_EDEC)));
         if (fuse) {
           TcLayer& L = ch.layer[1];
+          if (p->S_dec.p) L.seg_add = p->S_dec.p, L.seg_add_bound = sl(p, SL_SDEC);
           L.seg_dst = p->dec_dst.p, L.seg_out = p->agg_grid.p, L.seg_ld = De, L.seg_rows = No, L.seg_carry = p->seg_carry.p;
           L.seg_maxdeg = (float)p->dec_maxdeg, L.seg_bound = sl(p, SL_AGG_GRID);
           if (p->dec_mindeg == 0) GW_CUDA(cudaMemsetAsync(p->agg_grid.p, 0, (size_t)cb * No * De * sizeof(float), st));
@@ -1156,6 +1163,7 @@ int gw_plan_create(const gw_dims* dims, gw_plan** out_plan) {
   rc |= p->e_enc.alloc((size_t)d.n_in * De) | p->xm0.alloc((size_t)d.n_mesh * Dn) | p->C1_enc.alloc((size_t)d.n_in * He);
   rc |= p->e_lat.alloc((size_t)d.n_lat_edges * De) | p->e_dec.alloc((size_t)d.n_dec_edges * De);
   rc |= p->E1_dec.alloc((size_t)d.n_dec_edges * He) | p->tmpP.alloc((size_t)d.n_mesh * He);
+  if (tc && d.n_out > 0 && d.n_dec_edges > 0) rc |= p->S_dec.alloc((size_t)d.n_out * De);
   {  // hidden-activation ping-pong of run_mlp: every stage on the CUDA-core path, the one-off constant precompute
      // (one sample's worth of rows) on the tensor-core path
     size_t pp = (tc ? 1 : chunk) * max_rows * max_hid;
@@ -1199,7 +1207,7 @@ int gw_plan_destroy(gw_plan* p) {
   for (DevBuf<int32_t>* b : {&p->enc_mesh, &p->enc_perm, &p->enc_ptr, &p->lat_src, &p->lat_dst, &p->lat_ptr, &p->dec_src, &p->dec_ptr})
     b->release();
   for (DevBuf<float>* b : {&p->enc_attr, &p->lat_attr, &p->dec_attr, &p->wbuf, &p->zeros_h3, &p->e_enc, &p->xm0, &p->C1_enc,
-                           &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
+                           &p->e_lat, &p->e_dec, &p->E1_dec, &p->S_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e, &p->xbuf0,
                            &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     b->release();
   p->tc_packed.release(), p->tc_absmax.release(), p->agg_mesh.release(), p->agg_grid.release();
@@ -1225,7 +1233,7 @@ int64_t gw_plan_device_bytes(const gw_plan* p) {
   for (const DevBuf<int32_t>* b : {&p->enc_mesh, &p->enc_perm, &p->enc_ptr, &p->lat_src, &p->lat_dst, &p->lat_ptr, &p->dec_src, &p->dec_ptr})
     t += b->bytes();
   for (const DevBuf<float>* b : {&p->enc_attr, &p->lat_attr, &p->dec_attr, &p->wbuf, &p->zeros_h3, &p->e_enc, &p->xm0, &p->C1_enc,
-                                 &p->e_lat, &p->e_dec, &p->E1_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e,
+                                 &p->e_lat, &p->e_dec, &p->E1_dec, &p->S_dec, &p->tmpP, &p->bufA, &p->bufB, &p->rows_n, &p->rows_e,
                                  &p->xbuf0, &p->xbuf1, &p->ebuf0, &p->ebuf1, &p->P})
     t += b->bytes();
   t += p->tc_packed.bytes() + p->agg_mesh.bytes() + p->agg_grid.bytes() + p->seg_carry.bytes() + p->dec_dst.bytes();

@@ -94,6 +94,9 @@ struct TcLayer {
   int32_t seg_ld = 0, seg_rows = 0;
   float seg_maxdeg = 0.f;            // longest segment (bound of the sums)
   float* seg_bound = nullptr;        // device float set to the bound of the segment sums
+  const float* seg_add = nullptr;    // [seg_rows, seg_ld] or null: a per-target constant added to every complete sum (the sum of a
+                                     // constant residual over the target's rows, hoisted out of the row loop: gw_api.cu S_dec)
+  const float* seg_add_bound = nullptr;  // device float: magnitude bound of seg_add
 };
 
 struct TcChain {

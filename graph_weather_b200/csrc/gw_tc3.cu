@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           const bool again = l > 0 && ch.layer[l - 1].out_bound == L.out_bound;
           *L.out_bound = again ? fmaxf(*L.out_bound, mo) : mo;
         }
-        if (L.seg_bound) *L.seg_bound = mo * L.seg_maxdeg;
+        if (L.seg_bound) *L.seg_bound = mo * L.seg_maxdeg + ldbound(L.seg_add_bound);
       }
       float so = 1.f;
       if (L.feeds_next) {
@@ -842,6 +842,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       float mbf = 1.f, c1f = 0.f, e2f = 0.f, e4f = 0.f, kf = 0.f, k1f = 0.f;
       char* tail_p = nullptr;
       char* carry_p = nullptr;
+      const char* add_p = nullptr;
       if constexpr (has_seg) {
         int dprev = __shfl_up_sync(0xffffffffu, d1, 4);
         if (lr == 0) dprev = dprev_g;
@@ -870,6 +871,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         head_st = lr == 0 && !ba && bb && d0 >= 0;  // the previous group's run ends with my first row
         one_st = ba && bb && d0 >= 0;               // my first row is a run of its own (a target with a single row)
         one_any = __any_sync(0xffffffffu, one_st);
+        // per-target constant (a constant residual summed over the target's rows, once per weight set): the owner of a run adds it
+        if (L.seg_add && (ba || bb) && d1 >= 0)
+          add_p = reinterpret_cast<const char*>(L.seg_add + (size_t)(uint32_t)d1 * (size_t)L.seg_ld + fcofs);
       }
       // The accumulator chunk s+1 is fetched from TMEM while chunk s is processed.
       float vb[2][16] = {};
@@ -878,6 +882,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       static_for<0, NP>([&](auto sc_) {
         constexpr int s = decltype(sc_)::value;
         float(&v)[16] = vb[s & 1];
+        float sadd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if constexpr (has_seg) {
+          if (add_p) ld256(add_p + 256 * s, sadd);  // (requested a chunk's worth of arithmetic before it is needed)
+        }
         tmem_wait_ld_into(v);
         if constexpr (has_ln) tr.ev(2010 + s);
         if constexpr (s + 1 < NP) {
@@ -952,7 +960,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           if (one_any) {
             if (one_st && sts_on) {
               char* dp = reinterpret_cast<char*>(L.seg_out + ((size_t)bs * L.seg_rows + (size_t)(uint32_t)d0) * (size_t)L.seg_ld + fcofs);
-              st256(dp + 256 * s, H[0], H[1], H[2], H[3], H[4], H[5], H[6], H[7]);
+              float a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (L.seg_add) ld256(reinterpret_cast<const char*>(L.seg_add + (size_t)(uint32_t)d0 * (size_t)L.seg_ld + fcofs) + 256 * s, a1);
+              st256(dp + 256 * s, H[0] + a1[0], H[1] + a1[1], H[2] + a1[2], H[3] + a1[3], H[4] + a1[4], H[5] + a1[5], H[6] + a1[6], H[7] + a1[7]);
             }
           }
 #pragma unroll
@@ -970,7 +980,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
               T[t] = fmaf(e4f, __shfl_down_sync(0xffffffffu, g2, 16), T[t]);
             }
           }
-          if (tail_st && sts_on) st256(tail_p + 256 * s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7]);
+          if (tail_st && sts_on)  // (sadd is zero for the threads that write a carry row or own no run)
+            st256(tail_p + 256 * s, T[0] + sadd[0], T[1] + sadd[1], T[2] + sadd[2], T[3] + sadd[3], T[4] + sadd[4], T[5] + sadd[5], T[6] + sadd[6],
+                  T[7] + sadd[7]);
         }
         if constexpr (feeds) {
           const uint32_t slot = (fi + s) % A_SLOTS;
@@ -1038,6 +1050,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
             GW_LF4(F_LN | F_RES | F_OUT);                // last layer of an edge / node MLP
             GW_LF4(F_LN | F_RES | F_OUT | F_SEG);        // ... of the processor's edge MLP: e' rows and their per-node sums
             GW_LF4(F_LN | F_RES | F_SEG);                // ... of the decoder's edge MLP: per-point sums only, e' is never written
+            GW_LF4(F_LN | F_SEG);                        // ... with its constant residual hoisted into a per-point constant (seg_add)
             GW_LF4(F_LN | F_RES | F_OUT | F_FEEDS);      // ... whose rows are also the operand of the next block's P products
             GW_LF4(F_LN | F_FEEDS);                      // LayerNorm feeding the next MLP of the same chain
             GW_LF4(F_OUT);                               // per-node products P = x W^T
@@ -1359,7 +1372,7 @@ static void tc3_mark_lean(TcChain& ch) {
     if (ok) ch.fast |= (int32_t)0x80000000u;
   }
   static const int kinds4[] = {F_ADD0 | F_ADD1 | F_RELU | F_FEEDS, F_ADD0 | F_RELU | F_FEEDS, F_RELU | F_FEEDS, F_LN | F_RES | F_OUT,
-                               F_LN | F_RES | F_OUT | F_SEG, F_LN | F_RES | F_SEG, F_LN | F_RES | F_OUT | F_FEEDS, F_LN | F_FEEDS, F_OUT,
+                               F_LN | F_RES | F_OUT | F_SEG, F_LN | F_RES | F_SEG, F_LN | F_SEG, F_LN | F_RES | F_OUT | F_FEEDS, F_LN | F_FEEDS, F_OUT,
                                F_RELU | F_OUT};
   static const int kinds2[] = {F_RELU | F_FEEDS, F_RELU | F_OUT};
   for (int l = 0; l < ch.n_layers; ++l) {
@@ -1370,6 +1383,7 @@ static void tc3_mark_lean(TcChain& ch) {
     if (L.residual.kind != SRC_NONE) ok = ok && src_fast(L.residual, L.N);
     if (L.out) ok = ok && aligned32(L.out) && !(L.ldo & 7) && L.out_cols >= L.N;
     if (L.seg_dst) ok = ok && L.seg_out && L.seg_carry && aligned32(L.seg_out) && aligned32(L.seg_carry) && !(L.seg_ld & 7) && L.ln_g && L.N == 256;
+    if (L.seg_add) ok = ok && L.seg_dst && aligned32(L.seg_add);
     ok = ok && L.Wp32 != nullptr;
     const int f = (L.add[0].kind != SRC_NONE ? F_ADD0 : 0) | (L.add[1].kind != SRC_NONE ? F_ADD1 : 0) | (L.relu ? F_RELU : 0) |
                   (L.ln_g ? F_LN : 0) | (L.residual.kind != SRC_NONE ? F_RES : 0) | (L.out ? F_OUT : 0) | (L.feeds_next ? F_FEEDS : 0) |
