@@ -106,7 +106,9 @@ int gw_plan_set_decoder_graph(gw_plan* plan, const int32_t* src, const int32_t* 
  * node_encoder(h3_nodes), the constant layer-1 terms).  Must follow the graph uploads; call again after any weight
  * or graph change.  `params` is a host array of n entries whose `data` are device pointers.  The table may hold
  * any subset of the groups "encoder.*", "processor.*", "decoder.*" (the reference's sub-modules can be built and
- * called on their own, tests/test_model.py:20-119); a stage whose group or graph is missing fails when called. */
+ * called on their own, tests/test_model.py:20-119); a stage whose group or graph is missing fails when called.
+ * "decoder.node_decoder" may end in a LayerNorm ("...model.{2 L + 1}.weight/bias" present): the regional forecaster builds
+ * its node decoder with the configured norm (regional_forecast.py:224-231), the forecaster / assimilator decoders without. */
 int gw_plan_set_weights(gw_plan* plan, const gw_param* params, int32_t n, void* stream);
 
 /* Replaces: GraphWeatherForecaster.forward (forecast.py:215-247, constraint_type="none") and
