@@ -131,7 +131,7 @@ struct gw_plan {
   DevBuf<float> P;            // [max_batch*n_mesh, 2*He]       per-node layer-1 products [W1s x | W1d x]
   size_t total_bytes = 0;
   // tensor-core path: packed weight images (UMMA operand layout) and their descriptors
-  struct TcW { const void* p = nullptr; const void* p32 = nullptr; int K = 0, N = 0, n_valid = 0; float winv = 1.f; float gain = 0.f; };  // gain = K * max|W|: |A.W^T| <= gain * max|A|
+  struct TcW { const void* p = nullptr; const void* p32 = nullptr; int K = 0, N = 0, N32 = 0, n_valid = 0; float winv = 1.f; float gain = 0.f; };  // gain = K * max|W|: |A.W^T| <= gain * max|A|
   struct TcMlp { TcW w0, w0b, w0c, w1, w2; };  // w0*: slices of the first Linear as each chain needs them
   DevBuf<unsigned char> tc_packed;
   DevBuf<float> tc_absmax;
@@ -296,7 +296,7 @@ static bool is_tc(const gw_plan* p) { return p->d.precision != GW_PREC_FP32_SIMT
 // layer = Linear `w` (+ bias b[l] of MLP m when l >= 0) (+ ReLU); magnitudes for the operand-range ladder travel along
 static TcLayer tc_layer(const gw_plan::TcW& w, const Mlp* m, int l, bool relu, bool feeds) {
   TcLayer L;
-  L.Wp = w.p, L.Wp32 = w.p32, L.K = w.K, L.N = w.N, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
+  L.Wp = w.p, L.Wp32 = w.p32, L.K = w.K, L.N = w.N, L.N32 = w.N32, L.n_valid = w.n_valid, L.wscale_inv = w.winv;
   L.bias = (m && l >= 0) ? m->b[l] : nullptr, L.relu = relu ? 1 : 0, L.feeds_next = feeds ? 1 : 0;
   L.gain = w.gain, L.off = (m && l >= 0 && (size_t)l < m->bmax.size()) ? m->bmax[l] : 0.f;
   return L;
@@ -496,7 +496,8 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
   size_t total = 0;
   for (size_t i = 0; i < n; ++i) {
     GW_CUDA(launch_absmax(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, p->tc_absmax.p + i, st));
-    total += 2 * ((tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024);  // two images: perm16 and perm32 feature order
+    total += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts, 1) + 1023) / 1024 * 1024;  // two images: perm16 and perm32 feature order
+    total += (tc_packed_bytes(reqs[i].K, reqs[i].N, parts, 2) + 1023) / 1024 * 1024;
   }
   for (size_t i = 0; i < nv; ++i) GW_CUDA(launch_absmax(vreqs[i].v, vreqs[i].n, vreqs[i].n, 1, p->tc_absmax.p + n + i, st));
   std::vector<float> amax(n + nv);
@@ -519,17 +520,19 @@ static int pack_tc_weights(gw_plan* p, cudaStream_t st) {
       scale = std::ldexp(1.f, 12 - e);   // amax * scale in [2048, 4096)
     }
     void* dst = p->tc_packed.p + off;
-    const size_t img = (tc_packed_bytes(reqs[i].K, reqs[i].N, parts) + 1023) / 1024 * 1024;
+    const size_t img = (tc_packed_bytes(reqs[i].K, reqs[i].N, parts, 1) + 1023) / 1024 * 1024;
+    const size_t img32 = (tc_packed_bytes(reqs[i].K, reqs[i].N, parts, 2) + 1023) / 1024 * 1024;
     GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, 1, dst, st));
     GW_CUDA(launch_pack_weights(reqs[i].W, reqs[i].ldw, reqs[i].K, reqs[i].N, scale, parts, 2, static_cast<unsigned char*>(dst) + img, st));
     reqs[i].out->p = dst;
     reqs[i].out->p32 = static_cast<unsigned char*>(dst) + img;
     reqs[i].out->K = (reqs[i].K + 63) / 64 * 64;
-    reqs[i].out->N = (reqs[i].N + 15) / 16 * 16;
+    reqs[i].out->N = tc_packed_rows(reqs[i].N, 1);
+    reqs[i].out->N32 = tc_packed_rows(reqs[i].N, 2);
     reqs[i].out->n_valid = reqs[i].N;
     reqs[i].out->winv = 1.f / scale;
     reqs[i].out->gain = (float)reqs[i].K * amax[i];
-    off += 2 * img;
+    off += img + img32;
   }
   return 0;
 }
@@ -966,6 +969,20 @@ static int stage_decoder(gw_plan* p, const float* x_in, int x_in_slot, const flo
           ch.layer[2].feeds_next = 1;
           ch.layer[3] = tc_layer(p->tc_dec_out.w0, &m, 0, true, true);
           ch.layer[4] = tc_layer(p->tc_dec_out.w1, &m, 1, true, true);
+          {  // the whole decoder tail as ONE lean chain when the output layer qualifies for the lean path's narrow epilogue (even
+             // out_dim, 8-byte aligned rows, no fused multi-GPU boundary): no hidden-row round trip, no general-path chain
+            TcChain c6 = ch;
+            c6.layer[5] = tc_layer(p->tc_dec_out.w2, &m, 2, false, false);
+            if (start && d.residual_dim > 0)
+              c6.layer[5].residual = src_stream(start + (size_t)s0 * No * start_ld, start_ld, d.out_dim, No);
+            tc_out(c6.layer[5], out + (size_t)s0 * No * out_ld, out_ld, d.out_dim);
+            c6.n_layers = 6;
+            apply_out_peers(p, c6);
+            if (tc3_chain_is_lean(c6)) {
+              GW_TRY(run_chain(p, c6, st));
+              continue;
+            }
+          }
           if (p->tc_dec_out.w1.N <= Dn && !(p->tc_dec_out.w1.N & 63)) {
             // the narrow output layer (78 of 80 columns, 8-byte aligned rows) would take the whole chain off the lean
             // path: run it as a chain of its own on the hidden rows h

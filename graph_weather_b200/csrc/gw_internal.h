@@ -40,9 +40,11 @@ cudaError_t launch_segsum(const float* base, int ld, int width, const int32_t* p
 
 // tcgen05 chain kernel (gw_tc3.cu)
 cudaError_t launch_chain_tc3(const TcChain& ch, cudaStream_t stream);
+bool tc3_chain_is_lean(const TcChain& ch);  // would the launch take the lean (perm32, 256-bit access) path?
 // Packs W[n, k] (n < N_src rows of stride ldw, k < K_src) into the UMMA operand image the chain kernel streams with
-// cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts).
-size_t tc_packed_bytes(int K_src, int N_src, int parts);
+// cp.async.bulk; `parts` = 2 (fp16 hi, lo) or 1 (bf16).  dst must hold tc_packed_bytes(K_src, N_src, parts, perm).
+size_t tc_packed_bytes(int K_src, int N_src, int parts, int perm);
+int tc_packed_rows(int N_src, int perm);  // rows of the packed image: N padded to 16 (perm16) or 64 (perm32)
 cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm, void* dst,
                                 cudaStream_t stream);  // perm: 1 = perm16 (general path), 2 = perm32 (lean path) feature order of gw_tc3.cu (gw_pack.cu)
 cudaError_t launch_absmax(const float* W, int ldw, int K_src, int N_src, float* out_max, cudaStream_t stream);

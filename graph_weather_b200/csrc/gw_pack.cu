@@ -15,8 +15,11 @@ namespace gw {
 // weight packing (one-off per weight set)
 // ------------------------------------------------------------------------------------------------------------------
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-size_t tc_packed_bytes(int K_src, int N_src, int parts) {
-  return (size_t)(round_up(K_src, 64) / 64) * parts * round_up(N_src, 16) * 128;
+// rows of a packed image: the perm16 image (general path) pads N to 16, the perm32 image (lean path: 64-column epilogue chunks)
+// to 64 -- only the forecast's 78-column output layer differs (80 vs 128 rows)
+int tc_packed_rows(int N_src, int perm) { return round_up(N_src, perm == 2 ? 64 : 16); }
+size_t tc_packed_bytes(int K_src, int N_src, int parts, int perm) {
+  return (size_t)(round_up(K_src, 64) / 64) * parts * tc_packed_rows(N_src, perm) * 128;
 }
 
 // dst image: for chunk kc, part p: panel of N rows x 128 B; element (n, k): 16B chunk ((k%64)/8) ^ (n&7), half k%8
@@ -31,9 +34,8 @@ __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int
   const size_t total = (size_t)Np * Kp;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(e / Kp), k = (int)(e % Kp);
-    // perm: 0 none, 1 perm16, 2 perm32 (rows: only when the padded row count is a multiple of 32 -- else perm16, which then is
-    // the last layer of a chain; K is always a multiple of 64)
-    const int ns = perm == 2 ? ((Np & 31) ? perm16_f(n) : perm32_f(n)) : (perm ? perm16_f(n) : n);
+    // perm: 0 none, 1 perm16, 2 perm32 (rows padded to 64, K is always a multiple of 64)
+    const int ns = perm == 2 ? perm32_f(n) : (perm ? perm16_f(n) : n);
     const int ks = perm == 2 ? perm32_f(k) : (perm ? perm16_f(k) : k);
     const float w = (ns < N_src && ks < K_src) ? W[(size_t)ns * ldw + ks] * wscale : 0.f;
     const int kc = k >> 6, kk = k & 63;
@@ -52,7 +54,7 @@ __global__ void gw_pack_weights_kernel(const float* __restrict__ W, int ldw, int
 
 cudaError_t launch_pack_weights(const float* W, int ldw, int K_src, int N_src, float wscale, int parts, int perm, void* dst,
                                 cudaStream_t stream) {
-  const int Kp = round_up(K_src, 64), Np = round_up(N_src, 16);
+  const int Kp = round_up(K_src, 64), Np = tc_packed_rows(N_src, perm);
   gw_pack_weights_kernel<<<256, 256, 0, stream>>>(W, ldw, K_src, N_src, Kp, Np, wscale, parts, perm, static_cast<uint8_t*>(dst));
   count_launch();
   return cudaGetLastError();

@@ -68,7 +68,7 @@ namespace t3 {
 enum { ABL_FENCE = 1, ABL_LOADS = 2, ABL_CONVERT = 4, ABL_STORES = 8, ABL_LN = 16, ABL_TMEM = 32, ABL_MMA = 64, ABL_WEIGHTS = 128 };
 
 // epilogue feature mask of a layer (TcLayer::kind); the lean path is instantiated for the masks that occur
-enum { F_ADD0 = 1, F_ADD1 = 2, F_RELU = 4, F_LN = 8, F_RES = 16, F_OUT = 32, F_FEEDS = 64, F_SEG = 128 };
+enum { F_ADD0 = 1, F_ADD1 = 2, F_RELU = 4, F_LN = 8, F_RES = 16, F_OUT = 32, F_FEEDS = 64, F_SEG = 128, F_NARROW = 256 };
 #ifndef GW_CHUNK_UNROLL
 #define GW_CHUNK_UNROLL 1  // the per-chunk loops stay rolled: unrolled, their code no longer fits the instruction cache
 #endif
@@ -321,7 +321,8 @@ __device__ __forceinline__ float srcbound(const RowSrc& s) {
   return s.bound_mul_i ? m * (float)max(__ldg(s.bound_mul_i), 1) : m;
 }
 
-// MODE 0: every part takes the general path; 1: every part takes the lean full-width path.  (A third mode that chose per
+// MODE 0: every part takes the general path; 1: every part takes the lean full-width path; 2: as 1, plus the forecast's narrow
+// output layer (layer_out_narrow) as the chain's last layer.  (A third mode that chose per
 // part inside one kernel was measured slower than the general path: the live state of both paths spills.)
 template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __grid_constant__ TcChain ch) {
@@ -1001,6 +1002,73 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
       if constexpr (feeds) fi += NP;
     };
 
+    // ---- the forecast's output layer on the lean path ---------------------------------------------------------------------------
+    // N is padded to 64 k columns of which n_valid (78) are real; the rows of the output and of the residual (the start features)
+    // are only 8-byte aligned: 64-bit accesses, one pair of columns at a time, warps whose 32 columns lie beyond n_valid idle.
+    // Keeping this layer in the node chain saves the hidden rows' round trip through HBM and a general-path chain per step.
+    auto layer_out_narrow = [&](auto /*instantiated in MODE 2 only*/, int l, uint32_t acc, uint32_t use, bool waited, int tile) {
+      const TcLayer& L = ch.layer[l];
+      const int bs = tile % batch, i0 = (tile / batch) * TILE_M;
+      const int nvalid = min(TILE_M, rows - i0);
+      const int np = L.N >> 6, nval = L.n_valid;
+      const float wsi = scl[2 * l];
+      const uint32_t bias_a = sbase + OFF_PAR + 4 * fcofs + l * 1024;
+      const uint32_t taddr = tmem_base + ftm + acc * 256;
+      const bool has_res = L.residual.kind != SRC_NONE;
+      const float* rp[2] = {nullptr, nullptr};
+      if (has_res) {
+        const float* base = reinterpret_cast<const float*>(src_sample_base(L.residual, bs));
+#pragma unroll
+        for (int m = 0; m < 2; ++m) rp[m] = base + (size_t)(uint32_t)(i0 + min(fr0 + m, nvalid - 1)) * (size_t)L.residual.ld;
+      }
+      float* op[2];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) op[m] = L.out + ((size_t)bs * rows + i0 + fr0 + m) * (size_t)L.ldo;
+      const bool st[2] = {fr0 < nvalid, fr0 + 1 < nvalid};
+      if (!waited) {
+        tr.ev(600 + l);
+        mbar_wait(bar_full_d + 8 * acc, use & 1, ch.status);
+        tc_fence_after();
+        tr.ev(610 + l);
+      }
+      for (int s = 0; s < np; ++s) {
+        const int c0 = 64 * s + fcofs;
+        const bool any = 64 * s + 32 * fc < nval;  // warp-uniform: my warp's 32 columns of this chunk hold real features
+        float2 r[2][4] = {};
+        if (any && has_res && !ABL3(ABL_LOADS)) {
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (c0 + 2 * g < nval) r[m][g] = __ldg(reinterpret_cast<const float2*>(rp[m] + c0 + 2 * g));
+        }
+        float v[16] = {};
+        if (any && !ABL3(ABL_TMEM)) {
+          tmem_ld_16x256b_x4(taddr + 64 * s, v);
+          tmem_wait_ld();
+        }
+        if (s + 1 == np) {  // my last read of this accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty_d + 8 * acc);
+        }
+        if (any) {
+          const float4 bl = lds128(bias_a + 256 * s), bh = lds128(bias_a + 256 * s + 16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], wsi, col8(bl, bh, i));
+          if (!ABL3(ABL_STORES)) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (st[m] && c0 + 2 * g < nval)  // (n_valid is even: a pair is inside or outside as a whole)
+                  *reinterpret_cast<float2*>(op[m] + c0 + 2 * g) = make_float2(v[4 * g + 2 * m] + r[m][g].x, v[4 * g + 2 * m + 1] + r[m][g].y);
+          }
+        }
+        tr.ev(700 + 10 * l + s);
+      }
+    };
+
     const int n_layers = ch.n_layers;
     bool first_tile = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, first_tile = false) {
@@ -1022,7 +1090,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
           // per-layer state is live: the assembly needs the registers.)
           const int t = l < 0 ? tile : next_tile;
           if (t < num_tiles) {
-            if constexpr (MODE == 1) {
+            if constexpr (MODE >= 1) {
               if (ch.a0[1].kind != SRC_NONE) stage0_fast(ic<4>{}, ic<4>{}, ic<0>{}, t);  // node chains: [x | aggregate]
               else if (ch.a0[0].kind == SRC_GATHER_BCAST_RELU) stage0_fast(ic<4>{}, ic<0>{}, ic<1>{}, t);  // decoder edges
               else if (ch.K0 == 256) stage0_fast(ic<4>{}, ic<0>{}, ic<0>{}, t);          // edge chains, products of x
@@ -1039,10 +1107,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gw_chain_tc3_kernel(const __gr
         }
         const TcLayer& L = ch.layer[l];
         const bool has_ln = L.ln_g != nullptr;
-        if constexpr (MODE == 1) {
+        if constexpr (MODE >= 1) {
 #define GW_LF(M, NP_) layer_fast(ic<(M)>{}, ic<(NP_)>{}, l, acc, use, last_layer, tile, ln_slot)
 #define GW_LF4(M) case (M): GW_LF(M, 4); break
 #define GW_LF24(M) case (M): if (L.N == 256) GW_LF(M, 4); else GW_LF(M, 2); break
+          bool narrow_done = false;
+          if constexpr (MODE == 2) {  // (a kernel of its own: with this layer compiled in, ptxas spills scalars in EVERY chain -- measured:
+                                      //  proc_edge +11 % -- so only the chain that ends in the forecast's output layer carries it)
+            if (L.kind & F_NARROW) {
+              layer_out_narrow(ic<0>{}, l, acc, use, last_layer, tile);
+              narrow_done = true;
+            }
+          }
+          if (!narrow_done)
           switch (L.kind) {
             GW_LF4(F_ADD0 | F_ADD1 | F_RELU | F_FEEDS);  // edge layer 1: gathered P[src] + P[dst]
             GW_LF4(F_ADD0 | F_RELU | F_FEEDS);           // encoder edge layer 1: broadcast constant term
@@ -1377,6 +1454,19 @@ static void tc3_mark_lean(TcChain& ch) {
   static const int kinds2[] = {F_RELU | F_FEEDS, F_RELU | F_OUT};
   for (int l = 0; l < ch.n_layers; ++l) {
     const TcLayer& L = ch.layer[l];
+    // the forecast's output layer: last layer, no activation / norm / addends, n_valid (even) real columns of an N32-row image,
+    // output and residual rows 8-byte aligned and not gathered
+    const bool narrow = l + 1 == ch.n_layers && L.n_valid < L.N32 && !(L.n_valid & 1) && !(L.N32 & 63) && L.N32 <= 256 && L.out && !L.relu &&
+                        !L.ln_g && !L.feeds_next && !L.seg_dst && L.add[0].kind == SRC_NONE && L.add[1].kind == SRC_NONE && L.Wp32 &&
+                        !(reinterpret_cast<uintptr_t>(L.out) & 7) && !(L.ldo & 1) && L.out_cols >= L.n_valid &&
+                        (L.residual.kind == SRC_NONE ||
+                         ((L.residual.kind == SRC_STREAM || L.residual.kind == SRC_BCAST) && L.residual.width >= L.n_valid && !(L.residual.ld & 1) &&
+                          !(reinterpret_cast<uintptr_t>(L.residual.base + L.residual.col0) & 7) && fits32(L.residual)));
+    if (narrow) {
+      ch.layer[l].kind = F_NARROW | F_OUT | (L.residual.kind != SRC_NONE ? F_RES : 0);
+      ch.fast |= 1 << l;
+      continue;
+    }
     bool ok = (L.N == 256 || L.N == 128) && L.n_valid == L.N;
     for (int a = 0; a < 2; ++a)
       if (L.add[a].kind != SRC_NONE) ok = ok && src_fast(L.add[a], L.N);
@@ -1398,6 +1488,15 @@ static void tc3_mark_lean(TcChain& ch) {
     if (ok && listed) ch.fast |= 1 << l;
   }
 }
+// Would launch_chain_tc3 run this chain on the lean path?  (gw_api.cu asks before it decides whether the forecast's 78-column output
+// layer rides in the node chain or runs as a general-path chain of its own.)
+bool tc3_chain_is_lean(const TcChain& ch_in) {
+  TcChain ch = ch_in;
+  tc3_mark_lean(ch);
+  if (getenv("GW_TC3_NOFAST")) return false;
+  const int32_t all = (int32_t)(0x80000000u | ((1u << ch.n_layers) - 1u));
+  return ch.fast == all && ch.out_mode == 0;
+}
 cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   TcChain ch = ch_in;
   using namespace t3;
@@ -1410,9 +1509,9 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     int n = 0;
     e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    const void* fns[4] = {(const void*)gw_chain_tc3_kernel<true, 0>, (const void*)gw_chain_tc3_kernel<true, 1>,
-                          (const void*)gw_chain_tc3_kernel<false, 0>, (const void*)gw_chain_tc3_kernel<false, 1>};
-    for (int i = 0; i < 4; ++i) {
+    const void* fns[6] = {(const void*)gw_chain_tc3_kernel<true, 0>,  (const void*)gw_chain_tc3_kernel<true, 1>,  (const void*)gw_chain_tc3_kernel<true, 2>,
+                          (const void*)gw_chain_tc3_kernel<false, 0>, (const void*)gw_chain_tc3_kernel<false, 1>, (const void*)gw_chain_tc3_kernel<false, 2>};
+    for (int i = 0; i < 6; ++i) {
       e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e != cudaSuccess) return e;
     }
@@ -1454,7 +1553,10 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
   int mode = ch.fast == all ? 1 : 0;
   if (ch.out_mode != 0) mode = 0;  // the multi-GPU boundary stores live in the general path's store tiers
   if (mode == 1)
-    for (int l = 0; l < ch.n_layers; ++l) ch.layer[l].Wp = ch.layer[l].Wp32;  // the lean path's feature order (perm32)
+    for (int l = 0; l < ch.n_layers; ++l) {  // the lean path's feature order (perm32) and row padding (64)
+      ch.layer[l].Wp = ch.layer[l].Wp32;
+      if (ch.layer[l].N32) ch.layer[l].N = ch.layer[l].N32;
+    }
   if (mode == 0)
     for (int l = 0; l < ch.n_layers; ++l)
       if (ch.layer[l].seg_dst) return cudaErrorInvalidValue;  // the fused per-target sum exists on the lean path only
@@ -1462,10 +1564,11 @@ cudaError_t launch_chain_tc3(const TcChain& ch_in, cudaStream_t stream) {
     if (ch.a0[a].kind == SRC_SEGSUM) return cudaErrorInvalidValue;  // reduce with gw_segsum_kernel first (a fused per-thread
                                                                     // reduction in stage 0 was measured slower than the kernel)
 #define GW_LAUNCH3(SPLIT_, MODE_) gw_chain_tc3_kernel<SPLIT_, MODE_><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ch)
+  if (mode == 1 && (ch.layer[ch.n_layers - 1].kind & F_NARROW)) mode = 2;
   if (ch.split) {
-    if (mode == 1) GW_LAUNCH3(true, 1); else GW_LAUNCH3(true, 0);
+    if (mode == 2) GW_LAUNCH3(true, 2); else if (mode == 1) GW_LAUNCH3(true, 1); else GW_LAUNCH3(true, 0);
   } else {
-    if (mode == 1) GW_LAUNCH3(false, 1); else GW_LAUNCH3(false, 0);
+    if (mode == 2) GW_LAUNCH3(false, 2); else if (mode == 1) GW_LAUNCH3(false, 1); else GW_LAUNCH3(false, 0);
   }
 #undef GW_LAUNCH3
   count_launch();
