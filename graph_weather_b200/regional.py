@@ -76,17 +76,17 @@ class BoundaryNudgingLayer(nn.Module):
 
     @staticmethod
     def _compute_relaxation_weights(lat_lons: list, device) -> torch.Tensor:
-        """Haversine distance from the region's centroid, normalised to [0, 1] (:92-130), [N, 1]."""
-        lats = torch.tensor([ll[0] for ll in lat_lons], dtype=torch.float32)
-        lons = torch.tensor([ll[1] for ll in lat_lons], dtype=torch.float32)
-        lats_rad, lons_rad = lats * (math.pi / 180.0), lons * (math.pi / 180.0)
-        center_lat, center_lon = lats_rad.mean(), lons_rad.mean()
-        dlat, dlon = lats_rad - center_lat, lons_rad - center_lon
-        a = torch.sin(dlat / 2) ** 2 + torch.cos(lats_rad) * torch.cos(center_lat) * torch.sin(dlon / 2) ** 2
-        dist = 2 * torch.asin(torch.sqrt(torch.clamp(a, 0.0, 1.0)))
-        max_dist = dist.max()
-        weights = dist / max_dist if max_dist > 0 else torch.zeros_like(dist)
-        return weights.unsqueeze(-1).to(device)
+        """[N, 1] relaxation prior (:92-130): great-circle distance of every coordinate from the centroid of the region (mean of
+        the latitudes / longitudes in radians), divided by the largest one -- 0 at the centre, 1 at the farthest point, all zeros
+        for a single point.  float32 throughout, like the reference."""
+        ll = torch.as_tensor(np.asarray(lat_lons, dtype=np.float32).reshape(-1, 2)) * (math.pi / 180.0)
+        lat, lon = ll[:, 0], ll[:, 1]
+        lat_c, lon_c = lat.mean(), lon.mean()
+        hav = torch.sin((lat - lat_c) / 2) ** 2 + torch.cos(lat) * torch.cos(lat_c) * torch.sin((lon - lon_c) / 2) ** 2
+        dist = 2 * torch.asin(torch.sqrt(hav.clamp(0.0, 1.0)))
+        far = dist.max()
+        prior = dist / far if far > 0 else torch.zeros_like(dist)
+        return prior.unsqueeze(-1).to(device)
 
 
 class _RegionGraphs:
@@ -132,21 +132,25 @@ class RegionalForecaster(nn.Module):
         self.nudging = BoundaryNudgingLayer(output_dim, c.nudging_hidden_dim) if c.enable_nudging else None
         self.graph_builder = DynamicGraphBuilder(resolution=c.resolution)
         self.h3_embeddings = nn.Parameter(torch.zeros(h3lite.get_num_cells(c.resolution), input_dim))
-        self.node_encoder = MLP(input_dim, c.node_dim, c.hidden_dim_processor_node, c.hidden_layers_processor_node, c.norm_type, c.use_checkpointing)
-        self.edge_encoder = MLP(2, c.edge_dim, c.hidden_dim_processor_edge, c.hidden_layers_processor_edge, c.norm_type, c.use_checkpointing)
-        self.encoder_gnn = GraphProcessor(1, c.node_dim, c.edge_dim, c.hidden_dim_processor_node, c.hidden_dim_processor_edge,
-                                          c.hidden_layers_processor_node, c.hidden_layers_processor_edge, c.norm_type)  # fmt: skip
-        self.latent_edge_encoder = MLP(2, c.edge_dim, c.hidden_dim_processor_edge, c.hidden_layers_processor_edge, c.norm_type, c.use_checkpointing)
-        self.processor = Processor(input_dim=c.node_dim, edge_dim=c.edge_dim, num_blocks=c.num_blocks,
-                                   hidden_dim_processor_edge=c.hidden_dim_processor_edge,
-                                   hidden_layers_processor_node=c.hidden_layers_processor_node,
-                                   hidden_dim_processor_node=c.hidden_dim_processor_node,
-                                   hidden_layers_processor_edge=c.hidden_layers_processor_edge, mlp_norm_type=c.norm_type,
-                                   precision=c.precision)  # fmt: skip
-        self.decoder_edge_encoder = MLP(2, c.edge_dim, c.hidden_dim_processor_edge, c.hidden_layers_processor_edge, c.norm_type, c.use_checkpointing)
-        self.decoder_gnn = GraphProcessor(1, c.node_dim, c.edge_dim, c.hidden_dim_processor_node, c.hidden_dim_processor_edge,
-                                          c.hidden_layers_processor_node, c.hidden_layers_processor_edge, c.norm_type)  # fmt: skip
-        self.node_decoder = MLP(c.node_dim, output_dim, c.hidden_dim_decoder, c.hidden_layers_decoder, c.norm_type, c.use_checkpointing)
+        hn, he, ln, le = c.hidden_dim_processor_node, c.hidden_dim_processor_edge, c.hidden_layers_processor_node, c.hidden_layers_processor_edge
+
+        def mlp(i, o, h, n):
+            return MLP(i, o, h, n, c.norm_type, c.use_checkpointing)
+
+        def block():  # one bipartite GNN block (encoder_gnn / decoder_gnn, :170-181, :211-222)
+            return GraphProcessor(1, c.node_dim, c.edge_dim, hn, he, ln, le, c.norm_type)
+
+        # registration order = the reference's (:158-231): it fixes the state_dict key order
+        self.node_encoder = mlp(input_dim, c.node_dim, hn, ln)
+        self.edge_encoder = mlp(2, c.edge_dim, he, le)
+        self.encoder_gnn = block()
+        self.latent_edge_encoder = mlp(2, c.edge_dim, he, le)
+        self.processor = Processor(input_dim=c.node_dim, edge_dim=c.edge_dim, num_blocks=c.num_blocks, hidden_dim_processor_edge=he,
+                                   hidden_layers_processor_node=ln, hidden_dim_processor_node=hn, hidden_layers_processor_edge=le,
+                                   mlp_norm_type=c.norm_type, precision=c.precision)  # fmt: skip
+        self.decoder_edge_encoder = mlp(2, c.edge_dim, he, le)
+        self.decoder_gnn = block()
+        self.node_decoder = mlp(c.node_dim, output_dim, c.hidden_dim_decoder, c.hidden_layers_decoder)  # WITH the norm (:224-231)
         self._base_dims = dict(
             in_dim=input_dim, enc_edge_attr_dim=2, out_dim=output_dim, residual_dim=output_dim, node_dim=c.node_dim, edge_dim=c.edge_dim,
             hidden_node=c.hidden_dim_processor_node, hidden_edge=c.hidden_dim_processor_edge,
