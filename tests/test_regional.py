@@ -102,3 +102,54 @@ def test_regional_forecaster_matches_reference_fixture(fx, precision):
     ref2 = restate.regional_forward(fx["sd"], g2, fx["x"][:, :300])
     assert float((o2.cpu() - ref2).abs().max()) < TOL
     assert torch.equal(m(x, fx["lat_lons"]), out)
+
+
+# ---- the reference's own test-suite for this model (/root/reference/tests/test_regional_forecast.py:11-199), same small config ----
+def _small_config(**kw):
+    from graph_weather_b200.regional import RegionalForecasterConfig
+
+    return RegionalForecasterConfig(feature_dim=12, aux_dim=4, node_dim=32, edge_dim=32, num_blocks=2, hidden_dim_processor_node=32,
+                                    hidden_dim_processor_edge=32, hidden_dim_decoder=32, **kw)  # fmt: skip
+
+
+_UK = [(51.5, -0.1), (52.0, 0.5), (53.0, -1.0), (54.0, -2.0), (50.0, -3.0)]
+_DE = [(52.5, 13.4), (48.1, 11.6), (50.9, 6.9)]
+
+
+def test_config_build_and_relaxation_weights():
+    """:35-41 and :178-184."""
+    from graph_weather_b200.regional import BoundaryNudgingLayer
+
+    model = _small_config().build()
+    assert hasattr(model, "forward") and hasattr(model, "graph_builder") and hasattr(model, "h3_embeddings")
+    assert model.nudging is None
+    w = BoundaryNudgingLayer._compute_relaxation_weights(_UK, torch.device("cpu"))
+    assert w.shape == (5, 1) and w.min() >= 0.0 and w.max() <= 1.0 and torch.isclose(w.max(), torch.tensor(1.0))
+
+
+@pytest.mark.gpu
+def test_reference_suite_small_config():
+    """:44-175: shapes, NaN-free, another region / another length on the same model, output_dim override, the residual with zero
+    weights, nudging off / without context / with context.  (Hidden size 32: the exact-fp32 CUDA-core path.)"""
+    torch.manual_seed(0)
+    model = _small_config().build().cuda().eval()
+    out = model(torch.randn(2, 5, 16, device="cuda"), _UK)
+    assert out.shape == (2, 5, 12) and not torch.isnan(out).any()
+    assert model(torch.randn(1, 3, 16, device="cuda"), _DE).shape == (1, 3, 12)
+    assert model(torch.randn(1, 5, 16, device="cuda"), _UK).shape == (1, 5, 12)
+    m6 = _small_config(output_dim=6).build().cuda().eval()
+    assert m6(torch.randn(1, 5, 16, device="cuda"), _UK).shape == (1, 5, 6)
+    x = torch.randn(1, 5, 16, device="cuda")
+    with torch.no_grad():
+        for q in model.parameters():
+            q.zero_()
+    assert torch.allclose(model(x, _UK), x[..., :12], atol=1e-5)  # :113-125
+    ctx = torch.randn(1, 5, 12, device="cuda") * 10.0
+    assert torch.allclose(model(x, _UK, global_context=ctx), model(x, _UK))  # nudging disabled: the context is ignored (:144-154)
+    mn = _small_config(enable_nudging=True, nudging_hidden_dim=16).build().cuda().eval()
+    o0 = mn(x, _UK, global_context=None)
+    assert o0.shape == (1, 5, 12) and not torch.isnan(o0).any()
+    assert not torch.allclose(o0, mn(x, _UK, global_context=ctx))  # :167-175
+    mt = _small_config().build().cuda()  # train mode + grad: the backward of this model is not built -- it says so (:87-99 is out of scope)
+    with torch.enable_grad(), pytest.raises(NotImplementedError):
+        mt(torch.randn(1, 5, 16, device="cuda"), _UK)
